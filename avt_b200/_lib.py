@@ -1,0 +1,80 @@
+"""ctypes binding of the C-ABI in include/avt_b200.h (the only way Python reaches the CUDA kernels).
+
+The shared library is built in-tree by `avt_b200.build` (nvcc, sm_100a). There is no fallback: if the
+library is missing or a call fails, a RuntimeError carrying avt_last_error() is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavt_b200.so")
+
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
+
+
+class Epilogue(C.Structure):
+    """Mirror of avt_epilogue_t."""
+    _fields_ = [
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("ldr", C.c_int64),
+        ("dact_z", C.c_void_p),
+        ("aux_z", C.c_void_p),
+        ("ldz", C.c_int64),
+        ("pos", C.c_void_p),
+        ("cls", C.c_void_p),
+        ("pos_period", C.c_int32),
+        ("act", C.c_int32),
+        ("dact", C.c_int32),
+        ("alpha", C.c_float),
+        ("drop_p", C.c_float),
+        ("drop_seed", C.c_uint64),
+        ("drop_offset", C.c_uint64),
+        ("out", C.c_void_p),
+        ("ldo", C.c_int64),
+        ("out_fp32", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]
+
+
+_lib = None
+
+_i64, _i32, _f32, _u64, _vp = C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_void_p
+
+# name -> argtypes; every function returns int (0 = ok) unless listed in _SPECIAL.
+SIGNATURES = {
+    "avt_check_device": [],
+    "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _vp],
+}
+_SPECIAL = {"avt_abi_version": ([], C.c_int), "avt_last_error": ([], C.c_char_p)}
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m avt_b200.build` (nvcc, sm_100a). "
+                "avt_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        for name, (argtypes, restype) in _SPECIAL.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().avt_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"avt_b200 {what} failed (code {rc}): {msg}")
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

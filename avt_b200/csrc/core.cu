@@ -1,0 +1,39 @@
+// Library plumbing: error string, device checks.
+#include <cstring>
+#include "common.cuh"
+
+namespace avt {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* what, const char* detail, const char* file, int line) {
+  snprintf(g_err, sizeof g_err, "%s: %s (%s:%d)", what, detail, file, line);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace avt
+
+extern "C" int avt_abi_version(void) { return 1; }
+extern "C" const char* avt_last_error(void) { return avt::g_err; }
+extern "C" int avt_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    avt::set_last_error("avt_check_device", "no CUDA device", __FILE__, __LINE__);
+    return AVT_ERR_NO_GPU;
+  }
+  if (major != 10) {
+    avt::set_last_error("avt_check_device", "device is not compute capability 10.x (B200)", __FILE__, __LINE__);
+    return AVT_ERR_NO_GPU;
+  }
+  return AVT_OK;
+}

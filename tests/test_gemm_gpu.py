@@ -1,0 +1,155 @@
+"""Parity of the tcgen05 GEMM (avt_gemm_bf16) against fp64 matmul on the same bf16-rounded operands.
+
+Tolerances (stated per the north star: bf16 path <= 1e-3 relative):
+  * fp32 output: rel-L2 <= 1e-5 (only fp32 accumulation-order noise; operands are exactly representable).
+  * bf16 output: every element within one bf16 rounding of the fp64 result: |err| <= 2^-8 |ref| + 1e-6 * scale.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from avt_b200 import ops
+    return ops
+
+
+def _mk(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda", dtype=torch.float32) * scale).to(torch.bfloat16)
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.double().t() if a_mn else a.double()
+    B = b.double().t() if b_mn else b.double()
+    return A @ B.t()
+
+
+def _check(out, ref, what=""):
+    ref = ref.double()
+    o = out.double()
+    scale = ref.abs().max().item() + 1e-30
+    if out.dtype == torch.float32:
+        rel = ((o - ref).norm() / (ref.norm() + 1e-30)).item()
+        assert rel <= 1e-5, f"{what}: rel-L2 {rel:.3e}"
+    else:
+        err = (o - ref).abs()
+        tol = ref.abs() * 2.0**-8 + 1e-6 * scale
+        bad = (err > tol).sum().item()
+        assert bad == 0, f"{what}: {bad} elements off by more than one bf16 ulp; max err {err.max().item():.3e} scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 256), (128, 64, 64, 64), (256, 512, 256, 256), (384, 384, 192, 128),
+    (200, 768, 768, 256), (80, 2048, 768, 64), (1000, 1024, 80, 128), (15760, 768, 768, 256),
+])
+def test_gemm_layouts(a_mn, b_mn, M, N, K, bn):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = _mk((K, M) if a_mn else (M, K), g)
+    b = _mk((K, N) if b_mn else (N, K), g)
+    if a_mn and M % 8:
+        pytest.skip("transposed A needs M % 8 == 0 (16-byte row pitch)")
+    for dt in (torch.float32, torch.bfloat16):
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+        ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+        torch.cuda.synchronize()
+        _check(out, _ref(a, b, a_mn, b_mn), f"M{M} N{N} K{K} bn{bn} a_mn{a_mn} b_mn{b_mn} {dt}")
+
+
+def _gelu_tanh(x):
+    return 0.5 * x * (1 + torch.tanh(math.sqrt(2 / math.pi) * (x + 0.044715 * x**3)))
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_bias_act_aux(act):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 300, 512, 256
+    a, b = _mk((M, K), g), _mk((N, K), g, 0.1)
+    bias = torch.randn(N, generator=g, device="cuda")
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, bias=bias, act=act, aux_z=z)
+    pre = _ref(a, b, False, False) + bias.double()
+    _check(z, pre, "aux_z")
+    want = torch.nn.functional.gelu(pre) if act == 1 else _gelu_tanh(pre)
+    err = (out.double() - want).abs()
+    assert (err <= want.abs() * 2.0**-7 + 2e-3).all(), err.max().item()
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_dact(act):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    M, N, K = 256, 256, 128
+    a, b = _mk((M, K), g), _mk((N, K), g, 0.1)
+    z = _mk((M, N), g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, dact_z=z, dact=act)
+    zz = z.double().requires_grad_(True)
+    y = torch.nn.functional.gelu(zz) if act == 1 else _gelu_tanh(zz)
+    (dz,) = torch.autograd.grad(y.sum(), zz)
+    want = _ref(a, b, False, False) * dz
+    rel = ((out.double() - want).norm() / want.norm()).item()
+    assert rel < 1e-4, rel
+
+
+def test_gemm_residual_accumulate_splitk():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M, N, K = 384, 768, 4096
+    a, b = _mk((K, M), g), _mk((K, N), g, 0.05)
+    ref = _ref(a, b, True, True)
+    res = torch.randn(M, N, generator=g, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, residual=res)
+    _check(out, ref + res.double(), "residual")
+    out = res.clone()
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, accumulate=True)
+    _check(out, ref + res.double(), "accumulate")
+    out = res.clone()
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, split_k=7)
+    _check(out, ref + res.double(), "split_k")
+
+
+def test_gemm_pos_cls():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    frames, period, N, K = 3, 197, 256, 128
+    M = frames * period
+    a, b = _mk((M, K), g), _mk((N, K), g, 0.1)
+    bias = torch.randn(N, generator=g, device="cuda")
+    pos = torch.randn(period, N, generator=g, device="cuda")
+    cls = torch.randn(N, generator=g, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, out, bias=bias, pos=pos, cls=cls, pos_period=period)
+    want = (_ref(a, b, False, False) + bias.double()).view(frames, period, N)
+    want[:, 0] = cls.double()
+    want = want + pos.double()
+    _check(out, want.view(M, N), "pos/cls")
+
+
+def test_gemm_dropout_statistics():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, N, K = 512, 1024, 64
+    a, b = _mk((M, K), g), _mk((N, K), g)
+    out0 = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, out0)
+    p = 0.1
+    out1 = torch.empty(M, N, device="cuda")
+    out2 = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, out1, drop_p=p, drop_seed=123, drop_offset=1000)
+    ops.gemm(a, b, out2, drop_p=p, drop_seed=123, drop_offset=1000)
+    assert torch.equal(out1, out2)  # same (seed, offset) -> same mask
+    kept = out1 != 0
+    rate = 1.0 - kept.float().mean().item()
+    assert abs(rate - p) < 0.005, rate
+    assert torch.allclose(out1[kept], out0[kept] / (1 - p), rtol=1e-5, atol=1e-6)
+    out3 = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, out3, drop_p=p, drop_seed=124, drop_offset=1000)
+    assert not torch.equal(out1 != 0, out3 != 0)
