@@ -45,8 +45,21 @@ _i64, _i32, _f32, _u64, _vp = C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_voi
 SIGNATURES = {
     "avt_check_device": [],
     "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _vp],
+    "avt_layernorm_fwd": [_vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
+    "avt_layernorm_bwd": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
+                          _i32, _vp, _i64, _vp],
+    "avt_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "avt_patchify_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "avt_colsum_bf16": [_vp, _i64, _i32, _i64, _vp, _vp],
+    "avt_frame_sum_grads": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
+    "avt_dropout_apply": [_vp, _i64, _f32, _u64, _u64, _vp, _vp, _vp],
+    "avt_attention_simt_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp],
+    "avt_attention_tc_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
+    "avt_attention_tc_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
+    "avt_attention_simt_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp],
 }
-_SPECIAL = {"avt_abi_version": ([], C.c_int), "avt_last_error": ([], C.c_char_p)}
+_SPECIAL = {"avt_abi_version": ([], C.c_int), "avt_last_error": ([], C.c_char_p),
+            "avt_layernorm_bwd_workspace_bytes": ([_i64, _i32], C.c_int64)}
 
 
 def lib():

@@ -1,0 +1,276 @@
+"""Host-side sequencing of the CUDA kernels for the two transformer stacks on the AVT hot path.
+
+`ParamPack`   flat fp32 master / bf16 shadow / fp32 gradient buffers (one allocation each, 256-byte aligned
+              slices) so that weights are down-cast by one kernel and gradients all-reduce as one message.
+`BlockStack`  pre-LN transformer blocks, forward + backward, shared by
+              * AVT-b  = timm VisionTransformer blocks (nn.Linear [out,in] weights, erf-GELU, LN eps 1e-6,
+                         full attention over 197 tokens)                       [SURVEY.md §3.3]
+              * AVT-h  = HF GPT2Block (Conv1D [in,out] weights, gelu_new, LN eps 1e-5, causal attention,
+                         attn/resid dropout)                                    [SURVEY.md §3.3b]
+torch is used here only to own device memory and streams; every arithmetic step is an `ops.*` call into the
+C-ABI. No autograd, no torch math.
+"""
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+_ALIGN = 64  # elements: 256 B in fp32, 128 B in bf16 (TMA needs 16 B; swizzled tiles like 128 B)
+
+
+class ParamPack:
+    """Owns flat buffers for a fixed list of named parameters and re-points the nn.Parameters into them."""
+
+    def __init__(self, named_params, device):
+        named_params = list(named_params)
+        # small tensors (biases, LayerNorm, cls/pos) first: their gradients are produced by atomics and need
+        # zero-initialisation each backward; the big matrices are overwritten by the wgrad GEMMs.
+        small = [(n, p) for n, p in named_params if p.dim() < 2 or p.numel() < 1 << 14]
+        big = [(n, p) for n, p in named_params if not (p.dim() < 2 or p.numel() < 1 << 14)]
+        self.names, self.slices, self.shapes = [], {}, {}
+        off = 0
+        for n, p in small + big:
+            self.names.append(n)
+            self.slices[n] = (off, p.numel())
+            self.shapes[n] = tuple(p.shape)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            if n == (small[-1][0] if small else None):
+                self.small_end = off
+        if not small:
+            self.small_end = 0
+        self.total = off
+        self.device = device
+        self.w = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.b = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.params = {}
+        with torch.no_grad():
+            for n, p in small + big:
+                view = self.wv(n)
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                self.params[n] = p
+        self._ptrs = {n: p.data_ptr() for n, p in self.params.items()}
+        self.refresh_bf16()
+
+    def _view(self, buf, n):
+        o, k = self.slices[n]
+        return buf[o:o + k].view(self.shapes[n])
+
+    def wv(self, n):
+        return self._view(self.w, n)
+
+    def gv(self, n):
+        return self._view(self.g, n)
+
+    def bv(self, n):
+        return self._view(self.b, n)
+
+    def intact(self):
+        """False if someone re-allocated a parameter (e.g. module.to()) so the flat views are stale."""
+        return all(p.data_ptr() == self._ptrs[n] and p.device == self.w.device for n, p in self.params.items())
+
+    def refresh_bf16(self):
+        ops.cast_bf16(self.w, self.b)
+
+    def zero_small_grads(self):
+        if self.small_end:
+            self.g[:self.small_end].zero_()
+
+    def zero_all_grads(self):
+        self.g.zero_()
+
+    def attach_grads(self):
+        """Direct-gradient mode: make every param.grad a view of the flat gradient buffer."""
+        for n, p in self.params.items():
+            p.grad = self.gv(n)
+
+
+def param_grads(pack, names, params, direct):
+    """What an autograd.Function returns for its parameter inputs after the kernels filled pack.g.
+    direct=True : gradients live in pack.g and param.grad are views of it (re-attached if the optimizer
+                  set them to None); autograd gets None. One backward per step (grads are overwritten).
+    direct=False: standard autograd semantics (accumulation, DDP hooks): views of ONE cloned buffer."""
+    if direct:
+        for n, p in zip(names, params):
+            if p.requires_grad and p.grad is None:
+                p.grad = pack.gv(n)
+        return (None,) * len(names)
+    g = pack.g.clone()
+    out = []
+    for n, p in zip(names, params):
+        o, k = pack.slices[n]
+        out.append(g[o:o + k].view(pack.shapes[n]) if p.requires_grad else None)
+    return tuple(out)
+
+
+@dataclass
+class StackSpec:
+    dim: int
+    heads: int
+    layers: int
+    eps: float
+    act: int                 # ops.ACT_GELU_ERF | ops.ACT_GELU_TANH
+    conv1d: bool             # weights stored [in, out] (HF Conv1D) instead of [out, in] (nn.Linear)
+    causal: bool
+    names: dict              # keys: ln1, qkv, proj, ln2, fc1, fc2 -> format strings with {i}
+    p_attn: float = 0.0
+    p_resid: float = 0.0
+    attn_impl: str = "simt"  # "simt" | "tc" (tcgen05 kernel for N=197, hd=64)
+
+
+def _split_k_for(m_w, n_w, k_rows, block_n, sms=148):
+    tiles = ((m_w + 127) // 128) * ((n_w + block_n - 1) // block_n)
+    kblocks = (k_rows + 63) // 64
+    want = max(1, (2 * sms + tiles - 1) // tiles)
+    return max(1, min(want, max(1, kblocks // 8)))
+
+
+class BlockStack:
+    def __init__(self, spec: StackSpec, pack: ParamPack):
+        self.s, self.pack = spec, pack
+        self.ws = {}
+
+    # ------------------------------------------------------------------ linear helpers (both weight layouts)
+    def _fwd(self, x, wname, out, **ep):
+        ops.gemm(x, self.pack.bv(wname), out, b_mn=self.s.conv1d, **ep)
+
+    def _dgrad(self, dy, wname, out, **ep):
+        ops.gemm(dy, self.pack.bv(wname), out, b_mn=not self.s.conv1d, **ep)
+
+    def _wgrad(self, x, dy, wname, bname):
+        dW = self.pack.gv(wname)
+        rows = x.shape[0]
+        if self.s.conv1d:   # dW[in, out] = X^T dY
+            sk = _split_k_for(x.shape[1], dy.shape[1], rows, 256)
+            ops.gemm(x, dy, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=False)
+        else:               # dW[out, in] = dY^T X
+            sk = _split_k_for(dy.shape[1], x.shape[1], rows, 256)
+            ops.gemm(dy, x, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=False)
+        if bname is not None:
+            ops.colsum(dy, self.pack.gv(bname))
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, M, nb, ntok, train):
+        key = (M, nb, ntok, train)
+        w = self.ws.get(key)
+        if w is not None:
+            return w
+        s, dev = self.s, self.pack.device
+        D, L = s.dim, s.layers
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *shape, dt=bf: torch.empty(*shape, dtype=dt, device=dev)
+        nl = L if train else 1  # without grad only one layer's activations are live
+        w = {
+            "x": [e(M, D, dt=f32) for _ in range(2 * nl + 1)],   # x_in, x_mid per layer, final
+            "ln1": [e(M, D) for _ in range(nl)], "qkv": [e(M, 3 * D) for _ in range(nl)],
+            "att": [e(M, D) for _ in range(nl)], "lse": [e(nb * s.heads, ntok, dt=f32) for _ in range(nl)],
+            "ln2": [e(M, D) for _ in range(nl)], "z": [e(M, 4 * D) for _ in range(nl)],
+            "h": [e(M, 4 * D) for _ in range(nl)],
+            "st": [e(4, M, dt=f32) for _ in range(nl)],           # mean1, rstd1, mean2, rstd2
+        }
+        if train:
+            w.update({"dx": e(M, D, dt=f32), "dxb": e(M, D), "dz": e(M, 4 * D), "dln": e(M, D), "datt": e(M, D),
+                      "dqkv": e(M, 3 * D), "g": e(M, D),
+                      "lnws": torch.empty(ops.layernorm_bwd_workspace(M, D), dtype=torch.uint8, device=dev)})
+        self.ws[key] = w
+        return w
+
+    # ------------------------------------------------------------------ forward
+    def workspace(self, M, nb, ntok, train):
+        """Activation buffers for M = nb*ntok rows. The caller writes the stack input (fp32 residual
+        stream) into w["x"][0] before calling forward()."""
+        return self._workspace(M, nb, ntok, train)
+
+    @staticmethod
+    def _xbuf(w, train, k):
+        return w["x"][k] if train else w["x"][k % 3]
+
+    def forward(self, w, nb, ntok, train, rng=(0, 0), dropout=False):
+        """Runs all blocks on w["x"][0]; returns the fp32 residual stream after the last block.
+        train: keep every layer's activations for backward. dropout: apply spec.p_attn / p_resid."""
+        s, pk = self.s, self.pack
+        D = s.dim
+        hd = D // s.heads
+        scale = hd ** -0.5
+        seed, off = rng
+        p_attn = s.p_attn if dropout else 0.0
+        p_res = s.p_resid if dropout else 0.0
+        for i in range(s.layers):
+            j = i if train else 0
+            nm = {k: v.format(i=i) for k, v in s.names.items()}
+            st = w["st"][j]
+            xin, xmid, xout = (self._xbuf(w, train, 2 * i + k) for k in range(3))
+            ops.layernorm_fwd(xin, pk.wv(nm["ln1"] + ".weight"), pk.wv(nm["ln1"] + ".bias"), s.eps, w["ln1"][j], st[0], st[1])
+            self._fwd(w["ln1"][j], nm["qkv"] + ".weight", w["qkv"][j], bias=pk.wv(nm["qkv"] + ".bias"))
+            self._attn_fwd(w["qkv"][j], w["att"][j], w["lse"][j], nb, ntok, hd, scale, p_attn, seed, off + (4 * i << 28))
+            self._fwd(w["att"][j], nm["proj"] + ".weight", xmid, bias=pk.wv(nm["proj"] + ".bias"), residual=xin,
+                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 1) << 28))
+            ops.layernorm_fwd(xmid, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3])
+            self._fwd(w["ln2"][j], nm["fc1"] + ".weight", w["h"][j], bias=pk.wv(nm["fc1"] + ".bias"), act=s.act,
+                      aux_z=w["z"][j] if train else None)
+            self._fwd(w["h"][j], nm["fc2"] + ".weight", xout, bias=pk.wv(nm["fc2"] + ".bias"), residual=xmid,
+                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 2) << 28))
+        w["rng"] = (seed, off, p_attn, p_res)
+        w["dims"] = (nb, ntok)
+        return self._xbuf(w, train, 2 * s.layers)
+
+    def _attn_fwd(self, qkv, out, lse, nb, ntok, hd, scale, p, seed, off):
+        s = self.s
+        if s.attn_impl == "tc" and p == 0.0 and not s.causal and hd == 64 and ntok <= 208:
+            ops.attention_tc_fwd(qkv, out, lse, nb, s.heads, ntok, scale=scale)
+        else:
+            ops.attention_simt_fwd(qkv, out, lse, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
+                                   seed=seed, offset=off)
+
+    def _attn_bwd(self, qkv, att, dout, lse, dqkv, nb, ntok, hd, scale, p, seed, off):
+        s = self.s
+        if s.attn_impl == "tc" and p == 0.0 and not s.causal and hd == 64 and ntok <= 208:
+            ops.attention_tc_bwd(qkv, att, dout, lse, dqkv, nb, s.heads, ntok, scale=scale)
+        else:
+            ops.attention_simt_bwd(qkv, dout, lse, dqkv, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
+                                   seed=seed, offset=off)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, w, dx, dxb):
+        """dx fp32 [M, D] / dxb bf16 copy: gradient w.r.t. the stack output (updated in place to the gradient
+        w.r.t. the stack input). Parameter gradients are written into pack.g: matrices are overwritten
+        (or atomically accumulated by split-K units), biases are accumulated by atomics - the caller zeroes
+        the corresponding region of pack.g first (zero_all_grads / zero_small_grads)."""
+        s, pk = self.s, self.pack
+        M, D = dx.shape
+        nb, ntok = w["dims"]
+        seed, off, p_attn, p_res = w["rng"]
+        hd = D // s.heads
+        scale = hd ** -0.5
+        for i in reversed(range(s.layers)):
+            nm = {k: v.format(i=i) for k, v in s.names.items()}
+            st = w["st"][i]
+            xin, xmid = w["x"][2 * i], w["x"][2 * i + 1]
+            # ---- MLP branch: x_out = x_mid + drop(fc2(act(fc1(LN2(x_mid)))))
+            g = dxb
+            if p_res > 0.0:
+                g = w["g"]
+                ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 2) << 28), y_bf16=g)
+            self._wgrad(w["h"][i], g, nm["fc2"] + ".weight", nm["fc2"] + ".bias")
+            self._dgrad(g, nm["fc2"] + ".weight", w["dz"], dact_z=w["z"][i], dact=s.act)
+            self._wgrad(w["ln2"][i], w["dz"], nm["fc1"] + ".weight", nm["fc1"] + ".bias")
+            self._dgrad(w["dz"], nm["fc1"] + ".weight", w["dln"])
+            ops.layernorm_bwd(w["dln"], xmid, st[2], st[3], pk.wv(nm["ln2"] + ".weight"), dx,
+                              pk.gv(nm["ln2"] + ".weight"), pk.gv(nm["ln2"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb)
+            # ---- attention branch: x_mid = x_in + drop(proj(attn(qkv(LN1(x_in)))))
+            g = dxb
+            if p_res > 0.0:
+                g = w["g"]
+                ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 1) << 28), y_bf16=g)
+            self._wgrad(w["att"][i], g, nm["proj"] + ".weight", nm["proj"] + ".bias")
+            self._dgrad(g, nm["proj"] + ".weight", w["datt"])
+            self._attn_bwd(w["qkv"][i], w["att"][i], w["datt"], w["lse"][i], w["dqkv"], nb, ntok, hd, scale, p_attn, seed,
+                           off + (4 * i << 28))
+            self._wgrad(w["ln1"][i], w["dqkv"], nm["qkv"] + ".weight", nm["qkv"] + ".bias")
+            self._dgrad(w["dqkv"], nm["qkv"] + ".weight", w["dln"])
+            ops.layernorm_bwd(w["dln"], xin, st[0], st[1], pk.wv(nm["ln1"] + ".weight"), dx,
+                              pk.gv(nm["ln1"] + ".weight"), pk.gv(nm["ln1"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb)
+        return dx, dxb

@@ -68,3 +68,101 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
     _lib.call("avt_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
               C.byref(ep), split_k, block_n, _stream())
     return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, rows=None, x_stride=None):
+    """y = LN(x) (x fp32 [rows, D] with row stride x_stride; y bf16 or fp32 [rows, D])."""
+    _chk_cuda(x, gamma, beta, y)
+    D = gamma.numel()
+    rows = y.shape[0] if rows is None else rows
+    x_stride = x.stride(0) if x_stride is None else x_stride
+    _lib.call("avt_layernorm_fwd", _ptr(x), x_stride, _ptr(gamma), _ptr(beta), float(eps), rows, D, _ptr(y),
+              int(y.dtype == torch.float32), y.stride(0), _ptr(mean), _ptr(rstd), _stream())
+    return y
+
+
+def layernorm_bwd_workspace(rows, D):
+    return _lib.lib().avt_layernorm_bwd_workspace_bytes(rows, D)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace, *, dx_in=None, dx_bf16=None, rows=None,
+                  x_stride=None, dx_stride=None, dxb_stride=None, accumulate=False):
+    _chk_cuda(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace)
+    D = gamma.numel()
+    rows = dy.shape[0] if rows is None else rows
+    x_stride = x.stride(0) if x_stride is None else x_stride
+    dx_stride = dx_out.stride(0) if dx_stride is None else dx_stride
+    if dx_bf16 is not None and dxb_stride is None:
+        dxb_stride = dx_bf16.stride(0)
+    _lib.call("avt_layernorm_bwd", _ptr(dy), int(dy.dtype == torch.float32), dy.stride(0), _ptr(x), x_stride, _ptr(mean),
+              _ptr(rstd), _ptr(gamma), rows, D, _ptr(dx_in), _ptr(dx_out), dx_stride, _ptr(dx_bf16), dxb_stride or 0,
+              _ptr(dgamma), _ptr(dbeta), int(accumulate), _ptr(workspace), workspace.numel() * workspace.element_size(),
+              _stream())
+
+
+def cast_bf16(src, dst):
+    _chk_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    _lib.call("avt_cast_f32_to_bf16", _ptr(src), _ptr(dst), src.numel(), _stream())
+    return dst
+
+
+def patchify(video, out, patch):
+    """video fp32 [F, C, H, W] (contiguous) -> out bf16 [F*(P+1), C*patch*patch]."""
+    _chk_cuda(video, out)
+    F, Cc, H, W = video.shape
+    assert video.is_contiguous() and video.dtype == torch.float32 and out.dtype == torch.bfloat16
+    _lib.call("avt_patchify_bf16", _ptr(video), _ptr(out), F, Cc, H, W, patch, _stream())
+    return out
+
+
+def colsum(x, out):
+    """out[c] += sum_r x[r, c] (x bf16 2-D, out fp32)."""
+    _chk_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and x.stride(1) == 1
+    _lib.call("avt_colsum_bf16", _ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(out), _stream())
+
+
+def frame_sum_grads(dx, F, period, D, workspace, dpos=None, dcls=None, dbias=None, accumulate=False):
+    _chk_cuda(dx, workspace)
+    assert dx.dtype == torch.float32 and workspace.numel() >= period * D
+    _lib.call("avt_frame_sum_grads", _ptr(dx), F, period, D, _ptr(dpos), _ptr(dcls), _ptr(dbias), int(accumulate),
+              _ptr(workspace), _stream())
+
+
+def dropout_apply(x, p, seed, offset, y_f32=None, y_bf16=None):
+    _chk_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _lib.call("avt_dropout_apply", _ptr(x), x.numel(), float(p), int(seed), int(offset), _ptr(y_f32), _ptr(y_bf16), _stream())
+
+
+def attention_simt_fwd(qkv, out, lse, B, H, N, hd, *, causal, scale, drop_p=0.0, seed=0, offset=0):
+    _chk_cuda(qkv, out, lse)
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
+    _lib.call("avt_attention_simt_fwd", _ptr(qkv), _ptr(out), _ptr(lse), B, H, N, hd, int(causal), float(scale),
+              float(drop_p), int(seed), int(offset), _stream())
+
+
+def attention_simt_bwd(qkv, dout, lse, dqkv, B, H, N, hd, *, causal, scale, drop_p=0.0, seed=0, offset=0):
+    _chk_cuda(qkv, dout, lse, dqkv)
+    assert dout.dtype == torch.bfloat16 and dqkv.dtype == torch.bfloat16 and dout.is_contiguous() and dqkv.is_contiguous()
+    _lib.call("avt_attention_simt_bwd", _ptr(qkv), _ptr(dout), _ptr(lse), _ptr(dqkv), B, H, N, hd, int(causal),
+              float(scale), float(drop_p), int(seed), int(offset), _stream())
+
+
+def attention_tc_fwd(qkv, out, lse, F, H, N, *, scale):
+    """tcgen05 attention forward (head_dim 64, N <= 208, no mask)."""
+    _chk_cuda(qkv, out, lse)
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
+    assert qkv.shape == (F * N, 3 * H * 64)
+    _lib.call("avt_attention_tc_fwd", _ptr(qkv), _ptr(out), _ptr(lse), F, H, N, float(scale), _stream())
+
+
+def attention_tc_bwd(qkv, out, dout, lse, dqkv, F, H, N, *, scale):
+    """tcgen05 attention backward (head_dim 64, N <= 208, no mask)."""
+    _chk_cuda(qkv, out, dout, lse, dqkv)
+    assert dout.dtype == torch.bfloat16 and dqkv.dtype == torch.bfloat16 and dout.is_contiguous() and dqkv.is_contiguous()
+    assert out.is_contiguous() and qkv.is_contiguous()
+    _lib.call("avt_attention_tc_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), F, H, N, float(scale),
+              _stream())

@@ -79,6 +79,70 @@ typedef struct avt_epilogue {
 int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
                   int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, void* stream);
 
+/* y[r,:] = LayerNorm(x[r,:]) * gamma + beta over the last dim D (<= 2048, multiple of 4); one warp per row.
+ * x fp32 with row stride x_stride (elements) — a stride of tokens*D selects one token per frame (the CLS
+ * row for timm VisionTransformer.norm + x[:, 0]). y is bf16 (y_fp32 = 0) or fp32. mean / rstd ([rows],
+ * may be NULL) are saved for backward. Replaces torch.nn.LayerNorm in timm Block.norm1/norm2,
+ * VisionTransformer.norm (eps 1e-6) and HF GPT2Block.ln_1/ln_2, GPT2Model.ln_f (eps 1e-5). */
+int avt_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta, float eps, int64_t rows,
+                      int D, void* y, int y_fp32, int64_t y_stride, float* mean, float* rstd, void* stream);
+
+/* LayerNorm backward. dx_out = (dx_in ? dx_in : 0) + dLN(dy); optional bf16 copy of dx_out (the A operand
+ * of the next dgrad / wgrad GEMM); dgamma / dbeta are overwritten or accumulated. `workspace` must hold
+ * avt_layernorm_bwd_workspace_bytes(rows, D) bytes. Replaces autograd of torch.nn.LayerNorm + the
+ * residual-branch gradient add. */
+int64_t avt_layernorm_bwd_workspace_bytes(int64_t rows, int D);
+int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride, const float* x, int64_t x_stride,
+                      const float* mean, const float* rstd, const float* gamma, int64_t rows, int D, const float* dx_in,
+                      float* dx_out, int64_t dx_stride, void* dx_bf16, int64_t dxb_stride, float* dgamma, float* dbeta,
+                      int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* dst[i] = bf16(src[i]), i < n (weight down-cast of the fp32 master parameters). */
+int avt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* Re-tile frames for the patch-embedding GEMM: video fp32 [F, C, H, W] -> out bf16 [F*(P+1), C*ps*ps],
+ * P = (H/ps)*(W/ps); row f*(P+1) is zero (CLS slot), row f*(P+1)+1+p is patch p flattened as (c, kh, kw),
+ * the K order of Conv2d.weight.view(D, -1). Replaces the im2col inside timm PatchEmbed.proj (Conv2d with
+ * stride == kernel) + flatten(2).transpose(1, 2). */
+int avt_patchify_bf16(const float* video, void* out, int F, int C, int H, int W, int ps, void* stream);
+
+/* out[c] += sum_r x[r, c]  (x bf16 [rows, ld]): bias gradients of nn.Linear / Conv1D. */
+int avt_colsum_bf16(const void* x, int64_t rows, int cols, int64_t ld, float* out, void* stream);
+
+/* s[t, :] = sum_f dx[f*period + t, :] (dx fp32 [F*period, D]); then dpos (+)= s, dcls (+)= s[0],
+ * dbias (+)= sum_{t>=1} s[t] (each may be NULL). Gradients of timm pos_embed / cls_token /
+ * patch_embed.proj.bias, and of HF wpe rows (period = T). workspace: period*D floats. */
+int avt_frame_sum_grads(const float* dx, int F, int period, int D, float* dpos, float* dcls, float* dbias,
+                        int accumulate, float* workspace, void* stream);
+
+/* y = keep(seed, offset, i) ? x[i] / (1-p) : 0 over a dense tensor of n (multiple of 4) elements; the same
+ * (seed, offset) reproduces the mask a GEMM epilogue applied to a dense [M, N] output (i = r*N + c).
+ * Backward of torch.nn.Dropout (HF embd / resid dropout). Either output may be NULL. */
+int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* y_f32, void* y_bf16,
+                      void* stream);
+
+/* Multi-head attention on CUDA cores for short sequences / wide heads (AVT-h: T <= 16, head_dim 256..1024).
+ * qkv bf16 [B*N, 3*H*hd], column = s*H*hd + h*hd + d (timm Attention.qkv and HF c_attn packing);
+ * out bf16 [B*N, H*hd]; lse fp32 [B*H, N]. causal != 0 masks keys j > i. Dropout (drop_p) is applied to the
+ * softmax probabilities with element index ((b*H + h)*N + i)*N + j.
+ * Replaces HF GPT2Attention._attn (matmul, /sqrt(hd), causal mask, softmax, attn_dropout, matmul) and its
+ * autograd backward; also usable for timm Attention (N = 197, hd = 64, causal = 0). */
+int avt_attention_simt_fwd(const void* qkv, void* out, float* lse, int B, int H, int N, int hd, int causal, float scale,
+                           float drop_p, uint64_t seed, uint64_t offset, void* stream);
+int avt_attention_simt_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, int B, int H, int N, int hd,
+                           int causal, float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream);
+
+/* ViT spatial attention on tcgen05 tensor cores: out = softmax(Q K^T * scale) V per (frame, head), for
+ * N <= 208 tokens per frame and head_dim 64 (ViT-B/16, ViT-L/16: N = 197). Same qkv / out / lse layout as
+ * avt_attention_simt_*; no mask, no dropout (timm attn_drop = 0). S and O live in tensor memory, the
+ * 197x197 score matrix never reaches HBM. Replaces timm Attention.forward's q@k^T -> softmax -> attn@v. */
+int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int F, int H, int N, float scale, void* stream);
+/* Backward of the above: dqkv bf16 [F*N, 3*H*64] from qkv, the saved forward output `out`, dout and lse.
+ * Five tcgen05 contractions per (key tile, query half); P and dS are recomputed, never stored in HBM.
+ * Replaces autograd through timm Attention's matmul / softmax / matmul. */
+int avt_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int F, int H,
+                         int N, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
