@@ -89,5 +89,12 @@ def check(rc, what=""):
         raise RuntimeError(f"avt_b200 {what} failed (code {rc}): {msg}")
 
 
+# kernels launched per C-ABI call (for bench.py's `gpu_launches` claim)
+_KERNELS_PER_CALL = {"avt_layernorm_bwd": 2, "avt_frame_sum_grads": 2}
+launch_count = 0
+
+
 def call(name, *args):
+    global launch_count
     check(getattr(lib(), name)(*args), name)
+    launch_count += _KERNELS_PER_CALL.get(name, 1)

@@ -96,6 +96,7 @@ class VisionTransformer(nn.Module):
                 nn.init.trunc_normal_(m.weight, std=0.02)
                 nn.init.zeros_(m.bias)
         self.direct_grads = False   # True: backward writes param.grad (views of one flat buffer) itself
+        self._grads_ready_hook = None  # called at the end of backward (parallel.FlatDataParallel)
         self.attn_impl = "tc"
         self._pack = None
         self._stack = None
@@ -176,6 +177,8 @@ class VisionTransformer(nn.Module):
         ops.gemm(dxb, A, pk.gv("patch_embed.proj.weight").view(D, Kp), a_mn=True, b_mn=True, split_k=sk)
         ops.frame_sum_grads(dx, F, ntok, D, self._aux[("fsum", ntok)], dpos=pk.gv("pos_embed"), dcls=pk.gv("cls_token"),
                             dbias=pk.gv("patch_embed.proj.bias"), accumulate=False)
+        if self._grads_ready_hook is not None:
+            self._grads_ready_hook()
 
 
 def create_model(model_type, num_classes=0, **kw):

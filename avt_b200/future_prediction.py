@@ -134,6 +134,7 @@ class AVTh(nn.Module):
         self.future_pred_loss = _instantiate_loss(future_pred_loss)
         self.return_past_too = return_past_too
         self.direct_grads = False
+        self._grads_ready_hook = None
         self._pack = None
         self._stack = None
         self._step = 0
@@ -213,6 +214,8 @@ class AVTh(nn.Module):
         ops.gemm(gb, a["xb"], pk.gv("encoder.weight"), a_mn=True, b_mn=True)                 # dWenc = g^T feats
         dfeats = torch.empty(M, C, dtype=torch.float32, device=ddec.device)
         ops.gemm(gb, pk.bv("encoder.weight"), dfeats, b_mn=True)                             # dfeats = g Wenc
+        if self._grads_ready_hook is not None:
+            self._grads_ready_hook()
         return dfeats
 
     # ------------------------------------------------------------------ reference-compatible forward

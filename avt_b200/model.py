@@ -1,0 +1,60 @@
+"""Host-side mirror of the reference glue around the two hot-path modules, for running the AVT end-to-end
+configuration (expts/01_ek100_avt.txt) without Hydra: `models/base_model.py:140-220` (forward_singlecrop) with
+backbone = avt_b200.backbone.TIMMModel, temporal_aggregator = Identity, future_predictor =
+avt_b200.future_prediction.AVTh, classifier = nn.Linear, classifier_on_past = true; plus the loss arithmetic of
+`func/train_eval_ops.py:57-85` / `func/train.py:207-217`. Inside the reference itself none of this is needed:
+BaseModel instantiates the two modules through their `_target_` paths.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .backbone import TIMMModel
+from .future_prediction import AVTh
+
+EXPTS01_HEAD = dict(n_head=4, n_layer=6, output_len=1, inter_dim=2048, return_past_too=True,
+                    future_pred_loss={"_target_": "torch.nn.MSELoss"}, future_pred_loss_wt=1.0, avg_last_n=1)
+
+
+class AVTModel(nn.Module):
+    def __init__(self, model_type="vit_base_patch16_224", backbone_dim=768, num_classes=3806, dropout=0.2,
+                 head_kwargs=None):
+        super().__init__()
+        self.backbone = TIMMModel(1, model_type)
+        hk = dict(EXPTS01_HEAD)
+        hk.update(head_kwargs or {})
+        self.future_predictor = AVTh(backbone_dim, **hk)
+        self.dropout = nn.Dropout(dropout)
+        self.classifiers = nn.ModuleDict({"action": nn.Linear(backbone_dim, num_classes)})
+        self._initialize_weights()
+
+    def _initialize_weights(self):  # models/base_model.py:110-127
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0, 0.01)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, video, target_shape=None):
+        """video (B, #clips=T, C, T'=1, H, W) -> (outputs dict, aux_losses dict)."""
+        B, num_clips = video.size(0), video.size(1)
+        feats = self.backbone(video.flatten(0, 1))                      # base_model.py:153-154
+        feats = torch.mean(feats, [-1, -2]).permute((0, 2, 1))          # :157, :166
+        feats = feats.reshape((B, num_clips) + feats.shape[1:]).flatten(1, 2)   # :183-191
+        past, future, losses, _ = self.future_predictor(feats, target_shape)    # :196-197
+        out = {"past": past, "future": future}
+        out["past_logits/action"] = self.classifiers["action"](self.dropout(past))     # :203-207
+        out["logits/action"] = self.classifiers["action"](self.dropout(future))       # :215-216
+        return out, losses
+
+
+def training_loss(outputs, aux_losses, target, target_subclips):
+    """sum_k mean(loss_k), weights 1/1/1: CE(future), CE(past vs per-frame mode label, ignore_index -1), MSE feat
+    (func/train_eval_ops.py:57-85, loss_fn/multidim_xentropy.py:10-25, func/train.py:207-217, expts/01:1-2)."""
+    losses = {"cls_action": F.cross_entropy(outputs["logits/action"], target, ignore_index=-1, reduction="none")}
+    past_tgt = torch.mode(target_subclips, -1)[0]
+    pl = outputs["past_logits/action"]
+    losses["past_cls_action"] = F.cross_entropy(pl.flatten(0, 1), past_tgt.flatten(), ignore_index=-1,
+                                                reduction="none").view(past_tgt.shape)
+    losses.update(aux_losses)
+    return sum(torch.mean(v) for v in losses.values())

@@ -1,0 +1,74 @@
+"""Data parallelism for the hot path: one process per GPU, clips sharded over the batch, ONE gradient
+all-reduce (mean) per flat buffer per step over NCCL / NVLink — the B200-native restatement of the reference's
+DistributedDataParallel wrap (func/train.py:771-778; mean over ranks because lr is scaled by world size, :718).
+
+The AVT-h gradients (78 % of the bytes) are complete before the ViT backward starts, so their all-reduce is
+launched from a hook inside the head's backward and overlaps the whole backbone backward.
+"""
+import torch
+import torch.distributed as dist
+
+
+def allreduce_mean_(tensors, group=None, async_op=False):
+    """In-place mean over ranks of each tensor; returns work handles when async_op."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return []
+    ws = dist.get_world_size(group)
+    handles = []
+    for t in tensors:
+        if t.is_cuda:
+            h = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        else:  # gloo has no AVG
+            h = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if async_op:
+                h.wait()
+                h = None
+            t.div_(ws)
+        if async_op and h is not None:
+            handles.append(h)
+    return handles
+
+
+class FlatDataParallel:
+    """Wraps an avt_b200.model.AVTModel-like module whose backbone.model / future_predictor own flat buffers."""
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+        self.vit, self.head = model.backbone.model, model.future_predictor
+        self.vit.direct_grads = True
+        self.head.direct_grads = True
+        self._handles = []
+        self.head._grads_ready_hook = self._head_ready
+        self.vit._grads_ready_hook = self._vit_ready
+        self.other = [p for n, p in model.named_parameters()
+                      if not n.startswith("backbone.model.") and not n.startswith("future_predictor.")]
+
+    def broadcast_parameters(self):
+        """DDP-constructor semantics: every rank starts from rank 0's weights (valid after the first forward)."""
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            for t in [self.vit.flat_buffers()[0], self.head.flat_buffers()[0]] + [p.data for p in self.other]:
+                dist.broadcast(t, 0, group=self.group)
+
+    def _head_ready(self):
+        self._handles += allreduce_mean_([self.head.flat_buffers()[1]], self.group, async_op=True)
+
+    def _vit_ready(self):
+        self._handles += allreduce_mean_([self.vit.flat_buffers()[1]], self.group, async_op=True)
+
+    def finish_backward(self):
+        """Call after loss.backward(): reduces the remaining (torch-owned) gradients and waits for all handles."""
+        grads = [p.grad for p in self.other if p.grad is not None]
+        self._handles += allreduce_mean_(grads, self.group, async_op=True)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    def flat_parameter_groups(self):
+        """Three 'parameters' for a stock torch.optim optimizer: the two flat buffers (as leaf tensors whose .grad is
+        the flat gradient buffer) + the torch-owned rest. Valid after the first forward."""
+        out = []
+        for m in (self.vit, self.head):
+            w, g = m.flat_buffers()
+            w.grad = g
+            out.append(w)
+        return out, self.other
