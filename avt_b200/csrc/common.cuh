@@ -32,20 +32,50 @@ int num_sms();
 
 // ----------------------------------------------------------------------------- activations
 // timm ViT uses nn.GELU (erf); HF GPT-2 uses gelu_new (tanh approximation).
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Both are evaluated branch-free (epilogue warps interleave 32 independent elements per thread; a branchy
+// libm erff/tanhf serialises them and made the fused GEMM epilogue 4x slower than its main loop).
+//   erf : Abramowitz & Stegun 7.1.28, |abs err| <= 3e-7:  erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16, x >= 0
+//   tanh: 1 - 2 / (1 + exp(2u)), rel err ~1e-6 (ex2.approx + rcp.approx)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Phi(x) = 0.5 * (1 + erf(x / sqrt(2)))
+__device__ __forceinline__ float normal_cdf(float x) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  float p = fmaf(u, 0.0000430638f, 0.0002765672f);
+  p = fmaf(p, u, 0.0001520143f);
+  p = fmaf(p, u, 0.0092705272f);
+  p = fmaf(p, u, 0.0422820123f);
+  p = fmaf(p, u, 0.0705230784f);
+  p = fmaf(p, u, 1.0f);
+  p = p * p; p = p * p; p = p * p; p = p * p;     // ^16 (overflows to +inf for |x| > ~25: rcp -> 0, erf -> 1)
+  const float half_erf = 0.5f - 0.5f * fast_rcp(p);  // 0.5 * erf(|x|/sqrt2)
+  return 0.5f + copysignf(half_erf, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * normal_cdf(x); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float pdf = 0.39894228040143268f * fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2/2)/sqrt(2 pi)
+  return fmaf(x, pdf, normal_cdf(x));
+}
+__device__ __forceinline__ float fast_tanh(float u) {
+  const float e = fast_ex2(fminf(2.8853900817779268f * u, 80.0f));  // exp(2u), clamped (no inf/inf)
+  return 1.0f - 2.0f * fast_rcp(1.0f + e);
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = 0.79788456080286536f * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  return 0.5f * x * (1.0f + fast_tanh(u));
 }
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float x2 = x * x;
   const float u = 0.79788456080286536f * (x + 0.044715f * x * x2);
-  const float t = tanhf(u);
+  const float t = fast_tanh(u);
   const float du = 0.79788456080286536f * (1.0f + 3.0f * 0.044715f * x2);
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }

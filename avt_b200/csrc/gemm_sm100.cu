@@ -2,11 +2,11 @@
 //
 //   C[M,N] = epilogue(A[M,K] · B[N,K]^T)     fp32 accumulation in tensor memory (TMEM)
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor tiles of A and B into a 128B-swizzled smem ring
 //   warp 1      MMA issuer    : one lane issues tcgen05.mma 128 x BN x 16 per 32-byte K step; tcgen05.commit
 //                               releases smem slots and publishes the finished accumulator
-//   warps 2..5  epilogue      : tcgen05.ld the accumulator (one row per thread), apply the fused
+//   warps 2..9  epilogue      : tcgen05.ld the accumulator (one row per thread), apply the fused
 //                               epilogue (bias / GELU / dGELU / dropout / residual / pos-embed) and store
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Either operand may be K-major (rows of the contraction dim contiguous) or MN-major (transposed in
@@ -21,7 +21,8 @@ namespace avt {
 constexpr int kBM = 128;        // tile rows  (UMMA M)
 constexpr int kBK = 64;         // K per smem stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 template <int BN>
 struct GemmCfg {
@@ -65,7 +66,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -156,9 +157,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ============================== epilogue (warps 2..5) ==============================
+    // ============================== epilogue (warps 2..9) ==============================
     const avt_epilogue_t& ep = p.ep;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
     const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
@@ -172,7 +174,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
       const int pos_t = ep.pos_period > 0 ? row % ep.pos_period : 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c0, r);
         tmem_ld_wait();

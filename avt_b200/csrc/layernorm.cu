@@ -67,7 +67,7 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) [+ dx_in];  partial dgamma/dbeta per CTA.
 template <int VPT>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, VPT <= 8 ? 2 : 1)
 ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, const float* __restrict__ x, int64_t x_stride,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               int64_t rows, int D, const float* __restrict__ dx_in, float* __restrict__ dx_out, int64_t dx_stride,
@@ -77,11 +77,9 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, const
   const int64_t warp_global = (int64_t)blockIdx.x * kLnWarps + warp;
   const int64_t warp_stride = (int64_t)gridDim.x * kLnWarps;
   const float inv_d = 1.0f / (float)D;
-  float4 g[VPT], ag[VPT], ab[VPT];
+  float4 ag[VPT], ab[VPT];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    g[i] = c < D ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -103,7 +101,8 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, const
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
         ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
-        d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));  // L1-resident; frees 4*VPT registers
+        d[i].x *= g.x; d[i].y *= g.y; d[i].z *= g.z; d[i].w *= g.w;
         s1 += d[i].x + d[i].y + d[i].z + d[i].w;
         s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
       } else {
@@ -148,15 +147,24 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, const
   }
 }
 
-// out[c] (+)= sum_p partial[p][c]
-__global__ void ln_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int D, float* __restrict__ dgamma,
-                                          float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * D) return;
+// out[c] (+)= sum_p partial[p][c]; blockDim (32, 8): 32 columns per block, partials split 8 ways
+__global__ void __launch_bounds__(256)
+ln_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int D, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, int accumulate) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * 2 * D + c];
-  float* dst = c < D ? dgamma + c : dbeta + (c - D);
-  *dst = accumulate ? *dst + s : s;
+  if (c < 2 * D)
+    for (int p = threadIdx.y; p < nparts; p += 8) s += partial[(size_t)p * 2 * D + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    float* dst = c < D ? dgamma + c : dbeta + (c - D);
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 template <int VPT>
@@ -224,7 +232,7 @@ extern "C" int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride,
                          dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, rows, D, dx_in, dx_out, dx_stride,
                          reinterpret_cast<bf16*>(dx_bf16), dxb_stride, partial)));
   AVT_CUDA_OK(cudaGetLastError());
-  ln_reduce_partials_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(partial, blocks, D, dgamma, dbeta, accumulate);
+  ln_reduce_partials_kernel<<<(2 * D + 31) / 32, dim3(32, 8), 0, st>>>(partial, blocks, D, dgamma, dbeta, accumulate);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }

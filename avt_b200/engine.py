@@ -53,6 +53,7 @@ class ParamPack:
                 p.data = view
                 self.params[n] = p
         self._ptrs = {n: p.data_ptr() for n, p in self.params.items()}
+        self._sig = None
         self.refresh_bf16()
 
     def _view(self, buf, n):
@@ -72,8 +73,19 @@ class ParamPack:
         """False if someone re-allocated a parameter (e.g. module.to()) so the flat views are stale."""
         return all(p.data_ptr() == self._ptrs[n] and p.device == self.w.device for n, p in self.params.items())
 
+    def _signature(self):
+        return sum(p._version for p in self.params.values())
+
     def refresh_bf16(self):
-        ops.cast_bf16(self.w, self.b)
+        """Down-cast the master weights unless nothing touched them since the shadow was last written (torch
+        in-place ops bump the parameters' version counters; avt_sgd_step refreshes the shadow itself)."""
+        sig = self._signature()
+        if sig != self._sig:
+            ops.cast_bf16(self.w, self.b)
+            self._sig = sig
+
+    def shadow_is_current(self):
+        self._sig = self._signature()
 
     def zero_small_grads(self):
         if self.small_end:

@@ -42,6 +42,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
         N, Kb = b.shape
     assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
     assert tuple(out.shape) == (M, N), (out.shape, M, N)
+    if block_n == 0 and M <= 128:
+        block_n = 64          # weight-streaming GEMMs (AVT-h, M = B*T rows): more, narrower tiles -> more SMs pulling HBM
     ep = Epilogue()
     ep.bias = _ptr(bias)
     ep.residual = _ptr(residual)
@@ -166,3 +168,10 @@ def attention_tc_bwd(qkv, out, dout, lse, dqkv, F, H, N, *, scale):
     assert out.is_contiguous() and qkv.is_contiguous()
     _lib.call("avt_attention_tc_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), F, H, N, float(scale),
               _stream())
+
+
+def sgd_step(p, g, m, shadow, lr, momentum, weight_decay, nesterov, first):
+    _chk_cuda(p, g, m, shadow)
+    assert p.dtype == g.dtype == m.dtype == torch.float32 and p.numel() == g.numel() == m.numel()
+    _lib.call("avt_sgd_step", _ptr(p), _ptr(g), _ptr(m), _ptr(shadow), p.numel(), float(lr), float(momentum),
+              float(weight_decay), int(nesterov), int(first), _stream())

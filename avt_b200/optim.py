@@ -1,0 +1,38 @@
+"""Fused SGD for the flat AVT-b / AVT-h parameter buffers (reference: torch.optim.SGD built at func/train.py:743-747
+from conf/opt/optimizer/sgd.yaml; momentum 0.9, nesterov, expts/01:26-28). One kernel per flat buffer updates the fp32
+master weights, the momentum buffer and the bf16 shadow the GEMMs read; everything else (classifier) stays on a stock
+torch.optim.SGD with the same hyper-parameters."""
+import torch
+
+from . import ops
+
+
+class FlatSGD:
+    def __init__(self, flat_modules, other_params, lr, momentum=0.9, weight_decay=0.0, nesterov=True):
+        self.mods = list(flat_modules)
+        self.lr, self.momentum, self.wd, self.nesterov = lr, momentum, weight_decay, nesterov
+        self.m = [None] * len(self.mods)
+        other_params = list(other_params)
+        self.other = torch.optim.SGD(other_params, lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                     nesterov=nesterov) if other_params else None
+
+    @property
+    def param_groups(self):  # lr schedulers poke at this
+        return self.other.param_groups if self.other is not None else [{"lr": self.lr}]
+
+    def step(self):
+        if self.other is not None:
+            self.lr = self.other.param_groups[0]["lr"]
+        for i, mod in enumerate(self.mods):
+            pack = mod._pack
+            first = self.m[i] is None
+            if first:
+                self.m[i] = torch.empty_like(pack.w)
+            ops.sgd_step(pack.w, pack.g, self.m[i], pack.b, self.lr, self.momentum, self.wd, self.nesterov, first)
+            pack.shadow_is_current()
+        if self.other is not None:
+            self.other.step()
+
+    def zero_grad(self, set_to_none=True):
+        if self.other is not None:
+            self.other.zero_grad(set_to_none=set_to_none)

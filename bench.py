@@ -127,6 +127,7 @@ def run_ours(args):
     import torch.distributed as dist
     from avt_b200 import _lib, ops
     from avt_b200.model import AVTModel, training_loss
+    from avt_b200.optim import FlatSGD
     from avt_b200.parallel import FlatDataParallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -154,8 +155,8 @@ def run_ours(args):
         loss = training_loss(out, aux, target, sub)
         if state["opt"] is None:                                     # flat buffers exist after the first forward
             dp.broadcast_parameters()
-            flat, rest = dp.flat_parameter_groups()
-            state["opt"] = torch.optim.SGD(flat + rest, lr=1e-4 * world, momentum=0.9, nesterov=True, weight_decay=1e-6)
+            state["opt"] = FlatSGD([dp.vit, dp.head], dp.other, lr=1e-4 * world, momentum=0.9, nesterov=True,
+                                   weight_decay=1e-6)                 # expts/01:26-28, func/train.py:718
         for p in dp.other:
             p.grad = None
         loss.backward()

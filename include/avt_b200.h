@@ -143,6 +143,13 @@ int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int F, int H, i
 int avt_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int F, int H,
                          int N, float scale, void* stream);
 
+/* One SGD-with-momentum step over a flat parameter buffer, torch.optim.SGD semantics with dampening 0
+ * (conf/opt/optimizer/sgd.yaml, expts/01:26-28: momentum 0.9, nesterov, uniform weight decay): p, m updated in
+ * place, and the bf16 copy of p read by the GEMMs (p_bf16, may be NULL) refreshed in the same pass.
+ * Replaces optimizer.step() (func/train.py:233) for the flat AVT-b / AVT-h buffers. */
+int avt_sgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n, float lr, float momentum, float weight_decay,
+                 int nesterov, int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

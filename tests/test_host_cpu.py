@@ -1,0 +1,119 @@
+"""CPU-side tests (run with -m "not gpu"): C-ABI surface, drop-in module interfaces, host logic, data-parallel
+gradient averaging over gloo (world_size 2). No CUDA compute."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "avt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(avt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from avt_b200 import _lib
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/avt_b200.h but not exported"
+    bound = set(_lib.SIGNATURES) | set(_lib._SPECIAL)
+    assert set(names) == bound, set(names) ^ bound
+    assert _lib.lib().avt_abi_version() >= 1
+
+
+def test_no_gpu_reports_error_not_fallback():
+    from avt_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert _lib.lib().avt_check_device() == -3
+    assert b"CUDA" in _lib.lib().avt_last_error() or b"device" in _lib.lib().avt_last_error()
+
+
+def test_backbone_interface_matches_reference_timm_names():
+    from avt_b200 import backbone
+    from oracle import vit as o_vit
+    ours = backbone.TIMMModel(1, "vit_base_patch16_224")
+    ref = o_vit.create_model("vit_base_patch16_224")
+    a = {k: tuple(v.shape) for k, v in ours.model.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert a == b
+    assert hasattr(ours, "model")                       # train.init_from_model=[[backbone.model, ...]]
+    assert backbone.create_model("vit_large_patch16_224").embed_dim == 1024
+    with pytest.raises(RuntimeError):                   # no CPU path
+        ours(torch.zeros(1, 3, 1, 224, 224))
+    with pytest.raises(NotImplementedError):
+        backbone.TIMMModel(1, "resnet50")
+
+
+def test_avth_interface_matches_reference_names_and_errors():
+    from avt_b200 import future_prediction as fp
+    from oracle import avth as o_avth
+    kw = dict(output_len=1, inter_dim=128, n_head=4, n_layer=3, return_past_too=True, avg_last_n=1)
+    ours = fp.AVTh(64, future_pred_loss={"_target_": "torch.nn.MSELoss"}, future_pred_loss_wt=1.0, **kw)
+    ref = o_avth.AVTh(64, future_pred_loss="mse", **kw)
+    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert a == b
+    assert ours.output_dim == 64 and isinstance(ours.future_pred_loss, torch.nn.MSELoss)
+    assert ours.future_pred_loss.reduction == "none"
+    assert tuple(ours.gpt_model.h[0].attn.c_attn.weight.shape) == (128, 384)   # HF Conv1D: [in, out]
+    # BaseModel._initialize_weights only touches nn.Linear: encoder/decoder are, Conv1D containers are not
+    assert isinstance(ours.encoder, torch.nn.Linear) and not isinstance(ours.gpt_model.h[0].attn.c_attn, torch.nn.Linear)
+    with pytest.raises(RuntimeError):
+        ours(torch.zeros(2, 5, 64), (2,))
+    for bad in (dict(in_features=1), dict(in_features=64, assign_to_centroids="x"), dict(in_features=64, drop_last_n=1),
+                dict(in_features=64, quantize_before_rollout=True)):
+        with pytest.raises(NotImplementedError):
+            fp.AVTh(**bad)
+
+
+def test_split_k_heuristic():
+    from avt_b200.engine import _split_k_for
+    assert _split_k_for(3072, 768, 15760, 256) >= 4      # 72 output tiles on 148 SMs -> split the 15760-row contraction
+    assert _split_k_for(2048, 8192, 80, 256) == 1        # AVT-h wgrad: K = 80 rows, nothing to split
+    assert _split_k_for(768, 768, 15760, 256) <= 31
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from avt_b200.parallel import allreduce_mean_
+    torch.manual_seed(rank)
+    flat = [torch.full((1000,), float(rank + 1)), torch.arange(10, dtype=torch.float32) * (rank + 1)]
+    allreduce_mean_(flat)
+    q.put((rank, flat[0][0].item(), flat[1][3].item()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_mean_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, 1.5, 4.5), (1, 1.5, 4.5)]        # mean over ranks (DDP semantics, func/train.py:771-778)
+
+
+def test_bench_reference_arm_schema():
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--frames", "2"], capture_output=True, text=True, env=env, timeout=600)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

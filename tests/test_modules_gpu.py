@@ -1,0 +1,280 @@
+"""Module-level parity of the drop-in backbone / head (CUDA, bf16 tensor-core math) against the CPU oracle.
+
+Tolerance policy (stated once, used below). The north star asks for 1e-3 relative on the bf16 path; that bound is
+met at kernel level on identically-rounded operands (tests/test_gemm_gpu.py, test_kernels_gpu.py). At module level
+every GEMM operand is *stored* in bf16 (2^-9 relative rounding each), so an L-layer stack cannot be closer than a few
+1e-3 to an fp64 oracle — torch's own bf16 autocast of the oracle lands at 5e-3..9e-3 on these configs. The module
+tests therefore require rel-L2 <= 2e-2 for outputs and <= 4e-2 for parameter gradients against the fp64/fp32 oracle,
+AND that our error does not exceed 1.25x the error of torch-autocast-bf16 on the same inputs (we are consistently
+below it because the residual stream, LayerNorm statistics and softmax stay in fp32).
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import avth as o_avth
+from oracle import base_model as o_base
+from oracle import vit as o_vit
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+OUT_TOL, GRAD_TOL = 2e-2, 4e-2
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def stress_init(m, seed=0):
+    """O(1) attention logits / activations (the reference init N(0, 0.01) would hide attention bugs)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() >= 2 and not any(k in n for k in ("pos_embed", "cls_token", "wpe")):
+                conv1d = any(k in n for k in ("c_attn", "c_fc", "c_proj"))
+                fan_in = p.shape[0] if conv1d else p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
+            elif "norm" in n or "ln_" in n:
+                p.copy_((1.0 if n.endswith("weight") else 0.0) + 0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+
+
+def _vit_pair(model_type, init):
+    from avt_b200 import backbone
+    torch.manual_seed(0)
+    ref = o_vit.create_model(model_type)
+    if init == "stress":
+        stress_init(ref)
+    ours = backbone.create_model(model_type)
+    ours.load_state_dict(ref.state_dict())
+    return ours.cuda(), ref
+
+
+@pytest.mark.parametrize("model_type,F,init,dtype", [
+    ("vit_test_patch16_32", 3, "stress", torch.float64), ("vit_test_patch16_64", 2, "stress", torch.float64),
+    ("vit_test_patch16_64", 5, "default", torch.float64), ("vit_base_patch16_224", 2, "stress", torch.float32),
+])
+def test_backbone_forward_backward_vs_oracle(model_type, F, init, dtype):
+    ours, ref = _vit_pair(model_type, init)
+    img = o_vit.CONFIGS[model_type][0]
+    x = torch.randn(F, 3, img, img, generator=torch.Generator().manual_seed(1))
+    gy = torch.randn(F, ref.embed_dim, generator=torch.Generator().manual_seed(2))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ya = ref.cuda()(x.cuda()).float().cpu()
+    ref = ref.cpu().to(dtype)
+    yr = ref(x.to(dtype))
+    yr.backward(gy.to(dtype))
+    yo = ours(x.cuda())
+    yo.backward(gy.cuda())
+    e_ours, e_autocast = rel(yo, yr), rel(ya, yr)
+    assert e_ours <= OUT_TOL and e_ours <= 1.25 * e_autocast + 1e-4, (e_ours, e_autocast)
+    gr = dict(ref.named_parameters())
+    for n, p in ours.named_parameters():
+        assert p.grad is not None and rel(p.grad, gr[n].grad) <= GRAD_TOL, (n, rel(p.grad, gr[n].grad))
+
+
+def test_backbone_timm_wrapper_contract_and_no_grad_path():
+    """(B, C, T, H, W) -> (B, C', T, 1, 1) as models/video_classification.py:213-227; eval under no_grad
+    (func/train.py:357) uses the activation-free workspace and must agree with the training-mode forward."""
+    from avt_b200 import backbone
+    m = backbone.TIMMModel(1, "vit_test_patch16_32").cuda()
+    video = torch.randn(4, 3, 2, 32, 32, device="cuda")
+    y = m(video)
+    assert y.shape == (4, 64, 2, 1, 1) and y.requires_grad
+    with torch.no_grad():
+        y2 = m(video)
+    assert torch.equal(y, y2)
+    # frame (b, t) of the clip layout equals the same image pushed through the ViT alone
+    single = m.model(video[1, :, 1].unsqueeze(0).contiguous())
+    assert torch.equal(single[0], y[1, :, 1, 0, 0])
+
+
+def test_backbone_frames_are_independent_at_full_size():
+    """Size-independent property at the BASELINE shape: 80 frames of ViT-B/16 — every frame's feature is bit-identical
+    to running that frame in a 2-frame batch (no cross-frame leakage through tiles / padding rows)."""
+    from avt_b200 import backbone
+    torch.manual_seed(3)
+    m = backbone.create_model("vit_base_patch16_224").cuda()
+    stress_init(m, 4)
+    x = torch.randn(80, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        full = m(x)
+        sub = m(x[[0, 79]].contiguous())
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[[0, 79]], sub)
+
+
+def _avth_pair(C, Dh, nh, nl, **extra):
+    from avt_b200 import future_prediction as fp
+    torch.manual_seed(0)
+    kw = dict(output_len=1, inter_dim=Dh, n_head=nh, n_layer=nl, return_past_too=True, avg_last_n=1, **extra)
+    ref = o_avth.AVTh(C, future_pred_loss="mse", **kw)
+    stress_init(ref)
+    ours = fp.AVTh(C, future_pred_loss={"_target_": "torch.nn.MSELoss"}, future_pred_loss_wt=1.0, **kw)
+    ours.load_state_dict(ref.state_dict())
+    return ours.cuda(), ref
+
+
+@pytest.mark.parametrize("C,Dh,nh,nl,B,T,dtype", [
+    (64, 32, 2, 2, 2, 5, torch.float64), (64, 128, 2, 3, 3, 10, torch.float64), (2048, 768, 4, 6, 2, 10, torch.float32),
+    (768, 2048, 4, 6, 8, 10, torch.float32), (768, 2048, 8, 2, 2, 15, torch.float32),
+])
+def test_avth_forward_backward_vs_oracle(C, Dh, nh, nl, B, T, dtype):
+    ours, ref = _avth_pair(C, Dh, nh, nl)
+    ref = ref.to(dtype).eval()
+    ours.eval()   # dropout off: RNG streams cannot be matched; see test_avth_dropout_* for the train path
+    x = torch.randn(B, T, C, generator=torch.Generator().manual_seed(1))
+    g1 = torch.randn(B, T, C, generator=torch.Generator().manual_seed(2))
+    g2 = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    xr = x.clone().to(dtype).requires_grad_(True)
+    pr, fr, lr, _ = ref(xr, (B,))
+    ((pr * g1.to(dtype)).sum() + (fr * g2.to(dtype)).sum() + lr["feat"].mean()).backward()
+    xo = x.clone().cuda().requires_grad_(True)
+    po, fo, lo, _ = ours(xo, (B,))
+    ((po * g1.cuda()).sum() + (fo * g2.cuda()).sum() + lo["feat"].mean()).backward()
+    assert po.shape == (B, T, C) and fo.shape == (B, C) and lo["feat"].shape == (B, T - 1, C)
+    assert rel(po, pr) <= OUT_TOL and rel(fo, fr) <= OUT_TOL and rel(lo["feat"], lr["feat"]) <= OUT_TOL
+    assert rel(xo.grad, xr.grad) <= GRAD_TOL
+    gr = dict(ref.named_parameters())
+    for n, p in ours.named_parameters():
+        if n == "gpt_model.wpe.weight":
+            assert torch.count_nonzero(p.grad[T:]) == 0      # only positions 0..T-1 are used
+            assert rel(p.grad[:T], gr[n].grad[:T]) <= GRAD_TOL
+        else:
+            assert rel(p.grad, gr[n].grad) <= GRAD_TOL, (n, rel(p.grad, gr[n].grad))
+
+
+def test_avth_matches_reference_golden():
+    """Golden vectors produced by the UNMODIFIED reference AVTh + HF GPT2Model (oracle/gen_golden.py)."""
+    from avt_b200 import future_prediction as fp
+    g = torch.load(os.path.join(GOLDEN, "avth_ref_small.pt"))
+    m = fp.AVTh(g["in_features"], future_pred_loss={"_target_": "torch.nn.MSELoss"}, **g["cfg"])
+    m.load_state_dict(g["state"])
+    m.cuda().eval()
+    x = g["x"].clone().cuda().requires_grad_(True)
+    past, fut, losses, _ = m(x, (x.shape[0],))
+    assert rel(past, g["past"]) <= OUT_TOL and rel(fut, g["future"]) <= OUT_TOL and rel(losses["feat"], g["feat"]) <= OUT_TOL
+    ((past * g["g_past"].cuda()).sum() + (fut * g["g_future"].cuda()).sum() + losses["feat"].mean()).backward()
+    assert rel(x.grad, g["dx"]) <= GRAD_TOL
+    for n, p in m.named_parameters():
+        if n in g["grads"] and n != "gpt_model.wpe.weight":
+            assert rel(p.grad, g["grads"][n]) <= GRAD_TOL, n
+
+
+def test_full_model_matches_reference_golden():
+    """BaseModel-level parity through the glue: golden from the unmodified reference BaseModel/TIMMModel/AVTh."""
+    from avt_b200.model import AVTModel
+    g = torch.load(os.path.join(GOLDEN, "basemodel_ref_small.pt"))
+    m = AVTModel("vit_test_patch16_32", 64, 32, head_kwargs=g["head"])
+    m.load_state_dict(g["state"])
+    m.cuda().eval()
+    out, aux = m(g["video"].cuda(), target_shape=(g["video"].shape[0],))
+    for k in ("logits/action", "past_logits/action", "future", "past"):
+        assert rel(out[k], g["outputs"][k]) <= OUT_TOL, (k, rel(out[k], g["outputs"][k]))
+    assert rel(aux["feat"], g["feat"]) <= OUT_TOL
+    loss = out["logits/action"].square().mean() + out["past_logits/action"].square().mean() + aux["feat"].mean()
+    assert abs(loss.item() - g["loss"].item()) <= OUT_TOL * abs(g["loss"].item())
+    loss.backward()
+    for n, p in m.named_parameters():
+        if n in g["grads"] and "wpe" not in n:
+            assert rel(p.grad, g["grads"][n]) <= GRAD_TOL, (n, rel(p.grad, g["grads"][n]))
+
+
+def test_avth_causality_at_full_size():
+    """expts/01 head (768 -> 2048, 6 layers, 4 heads), B=8, T=10: perturbing frame t leaves every prediction made
+    from frames < t bit-identical (causal mask + row-independent GEMMs)."""
+    ours, _ = _avth_pair(768, 2048, 4, 6)
+    ours.eval()
+    x = torch.randn(8, 10, 768, device="cuda")
+    x2 = x.clone()
+    x2[:, 6:] += 0.5
+    with torch.no_grad():
+        p1, f1, _, _ = ours(x, (8,))
+        p2, f2, _, _ = ours(x2, (8,))
+    assert torch.equal(p1[:, :7], p2[:, :7])        # past[:, t] = decoded[:, t-1] depends on frames <= t-1
+    assert not torch.equal(p1[:, 7:], p2[:, 7:]) and not torch.equal(f1, f2)
+
+
+def test_avth_dropout_train_mode():
+    from avt_b200 import future_prediction as fp
+    ours, ref = _avth_pair(64, 128, 2, 2)
+    ours.train()
+    x = torch.randn(4, 10, 64, device="cuda", requires_grad=True)
+    p1, f1, l1, _ = ours(x, (4,))
+    (p1.sum() + f1.sum() + l1["feat"].mean()).backward()
+    assert torch.isfinite(x.grad).all() and all(torch.isfinite(p.grad).all() for p in ours.parameters())
+    p2, _, _, _ = ours(x, (4,))
+    assert not torch.equal(p1, p2)                   # a fresh Philox offset every forward
+    # all pdrop = 0 through the GPT2Config kwargs (models/future_prediction.py:69,89-93): train() == eval()
+    nodrop, _ = _avth_pair(64, 128, 2, 2, embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    nodrop.train()
+    a, _, _, _ = nodrop(x.detach(), (4,))
+    nodrop.eval()
+    b, _, _, _ = nodrop(x.detach(), (4,))
+    assert torch.equal(a, b)
+    # dropout is unbiased: the mean over many masks approaches the eval output
+    ours.eval()
+    with torch.no_grad():
+        e = ours(x.detach(), (4,))[0]
+        ours.train()
+        acc = torch.zeros_like(e)
+        for _ in range(64):
+            acc += ours(x.detach(), (4,))[0]
+    assert rel(acc / 64, e) < 0.25
+
+
+def test_direct_grad_mode_and_fused_sgd_match_torch_sgd():
+    """FlatDataParallel/FlatSGD path (what bench.py runs) == autograd grads + torch.optim.SGD on the same model."""
+    from avt_b200.model import AVTModel
+    from avt_b200.optim import FlatSGD
+    from avt_b200.parallel import FlatDataParallel
+    hk = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32, embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    torch.manual_seed(0)
+    a = AVTModel("vit_test_patch16_32", 64, 32, dropout=0.0, head_kwargs=hk)
+    b = AVTModel("vit_test_patch16_32", 64, 32, dropout=0.0, head_kwargs=hk)
+    stress_init(a)
+    b.load_state_dict(a.state_dict())
+    a, b = a.cuda().train(), b.cuda().train()
+    video = torch.randn(2, 4, 3, 1, 32, 32, device="cuda")
+
+    def loss_of(m):
+        out, aux = m(video, target_shape=(2,))
+        return out["logits/action"].square().mean() + out["past_logits/action"].square().mean() + aux["feat"].mean()
+
+    dp = FlatDataParallel(a)
+    opt_a = None
+    opt_b = torch.optim.SGD(b.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-3)
+    for _ in range(3):
+        la = loss_of(a)
+        if opt_a is None:
+            opt_a = FlatSGD([dp.vit, dp.head], dp.other, lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-3)
+        for p in dp.other:
+            p.grad = None
+        la.backward()
+        dp.finish_backward()
+        opt_a.step()
+        lb = loss_of(b)
+        opt_b.zero_grad()
+        lb.backward()
+        opt_b.step()
+        assert abs(la.item() - lb.item()) <= 1e-4 * abs(lb.item()) + 1e-6
+    pb = dict(b.named_parameters())
+    for n, p in a.named_parameters():
+        assert rel(p, pb[n]) < 1e-4, (n, rel(p, pb[n]))
+
+
+def test_state_dict_load_after_first_forward_updates_kernels():
+    from avt_b200 import backbone
+    m = backbone.create_model("vit_test_patch16_32").cuda()
+    x = torch.randn(2, 3, 32, 32, device="cuda")
+    with torch.no_grad():
+        y0 = m(x)
+        sd = {k: v + 0.05 * torch.randn_like(v) for k, v in m.state_dict().items()}
+        m.load_state_dict(sd)          # in-place copy into the flat buffer views; bf16 shadow must be refreshed
+        y1 = m(x)
+    ref = o_vit.create_model("vit_test_patch16_32")
+    ref.load_state_dict({k: v.cpu() for k, v in sd.items()})
+    assert not torch.equal(y0, y1) and rel(y1, ref(x.cpu())) <= OUT_TOL

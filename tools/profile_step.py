@@ -7,6 +7,7 @@ import torch
 
 import bench
 from avt_b200.model import AVTModel, training_loss
+from avt_b200.optim import FlatSGD
 from avt_b200.parallel import FlatDataParallel
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
@@ -21,8 +22,7 @@ for i in range(steps):
     out, aux = model(video, target_shape=(8,))
     loss = training_loss(out, aux, target, sub)
     if opt is None:
-        flat, rest = dp.flat_parameter_groups()
-        opt = torch.optim.SGD(flat + rest, lr=1e-4, momentum=0.9, nesterov=True, weight_decay=1e-6)
+        opt = FlatSGD([dp.vit, dp.head], dp.other, lr=1e-4, momentum=0.9, nesterov=True, weight_decay=1e-6)
     for p in dp.other:
         p.grad = None
     loss.backward()
