@@ -145,21 +145,24 @@ class VisionTransformer(nn.Module):
         if key not in self._aux:
             self._aux[key] = torch.empty(M, Kp, dtype=torch.bfloat16, device=x.device)
             self._aux[("fstat", F)] = torch.empty(2, F, dtype=torch.float32, device=x.device)
+            self._aux[("xcls", F)] = torch.empty(F, D, dtype=torch.float32, device=x.device)
             self._aux[("fsum", ntok)] = torch.empty(ntok * D, dtype=torch.float32, device=x.device)
         A = self._aux[key]
         ops.patchify(x, A, self.patch_size)
         ops.gemm(A, pk.bv("patch_embed.proj.weight").view(D, Kp), w["x"][0], bias=pk.wv("patch_embed.proj.bias"),
                  pos=pk.wv("pos_embed").view(ntok, D), cls=pk.wv("cls_token").view(D), pos_period=ntok)
-        xf = st.forward(w, F, ntok, train)
+        xmid, y = st.forward(w, F, ntok, train)
         feats = torch.empty(F, D, dtype=torch.float32, device=x.device)
         fst = self._aux[("fstat", F)]
-        ops.layernorm_fwd(xf, pk.wv("norm.weight"), pk.wv("norm.bias"), 1e-6, feats, fst[0], fst[1], rows=F,
-                          x_stride=ntok * D)
-        return feats, (w, xf, F)
+        xcls = self._aux[("xcls", F)]
+        # final residual add + LayerNorm on the CLS rows only (timm: norm(x)[:, 0]; the other 196 rows are dead)
+        ops.layernorm_fwd(xmid, pk.wv("norm.weight"), pk.wv("norm.bias"), 1e-6, feats, fst[0], fst[1], rows=F,
+                          x_stride=ntok * D, add=y, add_stride=ntok * D, x_out=xcls)
+        return feats, (w, xcls, F)
 
     def _run_backward(self, saved, dfeats):
         pk, st = self._pack, self._stack
-        w, xf, F = saved
+        w, xcls, F = saved
         ntok, D = self.num_tokens, self.embed_dim
         M = F * ntok
         Kp = self.in_chans * self.patch_size ** 2
@@ -169,8 +172,8 @@ class VisionTransformer(nn.Module):
         dx.zero_()
         dxb.zero_()
         fst = self._aux[("fstat", F)]
-        ops.layernorm_bwd(dfeats, xf, fst[0], fst[1], pk.wv("norm.weight"), dx, pk.gv("norm.weight"), pk.gv("norm.bias"),
-                          w["lnws"], dx_bf16=dxb, rows=F, x_stride=ntok * D, dx_stride=ntok * D, dxb_stride=ntok * D)
+        ops.layernorm_bwd(dfeats, xcls, fst[0], fst[1], pk.wv("norm.weight"), dx, pk.gv("norm.weight"), pk.gv("norm.bias"),
+                          w["lnws"], dx_bf16=dxb, rows=F, dx_stride=ntok * D, dxb_stride=ntok * D)
         st.backward(w, dx, dxb)
         A = self._aux[("patch", M)]
         sk = engine._split_k_for(D, Kp, M, 256)

@@ -16,7 +16,7 @@
 namespace avt {
 
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                      uint32_t box_outer);
+                      uint32_t box_outer, int swizzle_bytes);
 
 constexpr int kTcHd = 64;
 constexpr int kTcKeys = 208;            // MMA N extent / PV contraction length (multiple of 16)
@@ -477,8 +477,8 @@ extern "C" int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int 
   const int D = H * kTcHd;
   CUtensorMap tmQ, tmKV;
   const uint64_t rows = (uint64_t)F * N;
-  if (int rc = make_tmap_bf16_2d(&tmQ, qkv, 3ull * D, rows, 3ull * D, 64, 128)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tmKV, qkv, 3ull * D, rows, 3ull * D, 64, kTcKeys)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmQ, qkv, 3ull * D, rows, 3ull * D, 64, 128, 128)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmKV, qkv, 3ull * D, rows, 3ull * D, 64, kTcKeys, 128)) return rc;
   static bool configured = false;
   if (!configured) {
     AVT_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
@@ -498,8 +498,8 @@ extern "C" int avt_attention_tc_bwd(const void* qkv, const void* out, const void
   const int D = H * kTcHd;
   CUtensorMap tmQKV, tmDO;
   const uint64_t rows = (uint64_t)F * N;
-  if (int rc = make_tmap_bf16_2d(&tmQKV, qkv, 3ull * D, rows, 3ull * D, 64, kTcKeys)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tmDO, dout, (uint64_t)D, rows, (uint64_t)D, 64, kTcKeys)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmQKV, qkv, 3ull * D, rows, 3ull * D, 64, kTcKeys, 128)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmDO, dout, (uint64_t)D, rows, (uint64_t)D, 64, kTcKeys, 128)) return rc;
   static bool configured = false;
   if (!configured) {
     AVT_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmem));

@@ -2,92 +2,141 @@
 //
 //   C[M,N] = epilogue(A[M,K] · B[N,K]^T)     fp32 accumulation in tensor memory (TMEM)
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (persistent, one CTA per SM, 320 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor tiles of A and B into a 128B-swizzled smem ring
-//   warp 1      MMA issuer    : one lane issues tcgen05.mma 128 x BN x 16 per 32-byte K step; tcgen05.commit
-//                               releases smem slots and publishes the finished accumulator
-//   warps 2..9  epilogue      : tcgen05.ld the accumulator (one row per thread), apply the fused
-//                               epilogue (bias / GELU / dGELU / dropout / residual / pos-embed) and store
+//   warp 1      MMA issuer    : one lane issues tcgen05.mma (K = 16 per instruction); tcgen05.commit releases smem
+//                               slots and publishes the finished accumulator
+//   warps 2..9  epilogue      : tcgen05.ld the accumulator (one row per thread, two warps per TMEM lane quarter),
+//                               fused epilogue (bias / GELU (+ its derivative) / dropout / residual / pos-embed),
+//                               bf16 results leave through per-warp swizzled smem slots + TMA stores
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Either operand may be K-major (rows of the contraction dim contiguous) or MN-major (transposed in
-// memory): forward, dgrad and wgrad of nn.Linear and HF Conv1D all map onto this one kernel without
-// materialising a transpose. Split-K work units accumulate with fp32 atomics (weight gradients).
+//
+// CG = 2 ("CTA pair", cta_group::2): two CTAs of a cluster share one 256 x BN tile. Each CTA loads its own 128 rows
+// of A and HALF of the B tile; the leader CTA issues tcgen05.mma.cta_group::2 which reads both halves and writes
+// 128 rows of the accumulator into each CTA's TMEM. Per output element this cuts the L2->SM operand traffic by a
+// third (ncu: the 1-CTA 128x256 tile saturates the L2->SM fabric at ~10 TB/s with the tensor pipe 52 % active).
+//
+// Either operand may be K-major (contraction dim contiguous) or MN-major (transposed in memory): forward, dgrad and
+// wgrad of nn.Linear and HF Conv1D all map onto this one kernel without materialising a transpose. Split-K work
+// units accumulate with fp32 atomics (weight gradients).
 #include <cuda.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace avt {
 
-constexpr int kBM = 128;        // tile rows  (UMMA M)
+constexpr int kBM = 128;        // accumulator rows per CTA (UMMA M = 128 per CTA, 256 per pair)
 constexpr int kBK = 64;         // K per smem stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
-constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kSlotBytes = 2048;  // TMA-store staging slot: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
+constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kEpiBytes = kEpiWarps * 2 * kSlotBytes + 2 * BN * 4;  // staging slots + bias (double-buffered)
+  static constexpr int kBarBytes = 256;
+  static constexpr int kMaxStages = (kSmemLimit - kEpiBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes;
+  static_assert(kStages >= 3, "not enough shared memory for a 3-stage pipeline");
 };
 
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks, split_k, kb_per_split;
+  int tma_out;  // bf16 `out` (and aux_z) leave through TMA stores
   avt_epilogue_t ep;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ void act_and_grad(int act, float x, float& y, float& dy) {
+  if (act == AVT_ACT_GELU_ERF) {
+    const float cdf = normal_cdf(x);
+    const float pdf = 0.39894228040143268f * fast_ex2(-0.72134752044448170f * x * x);
+    y = x * cdf;
+    dy = fmaf(x, pdf, cdf);
+  } else if (act == AVT_ACT_GELU_TANH) {
+    const float x2 = x * x;
+    const float t = fast_tanh(0.79788456080286536f * (x + 0.044715f * x * x2));
+    const float du = 0.79788456080286536f * (1.0f + 3.0f * 0.044715f * x2);
+    y = 0.5f * x * (1.0f + t);
+    dy = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+  } else {
+    y = x;
+    dy = 1.0f;
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+template <int BN, int CG, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  using Cfg = GemmCfg<BN, CG>;
+  constexpr int BNL = BN / CG;  // B rows (N extent) held by this CTA
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sStageOut = smem + Cfg::kStages * Cfg::kStageBytes;            // [kEpiWarps][2][kSlotBytes]
+  float* sBias = reinterpret_cast<float*>(sStageOut + kEpiWarps * 2 * kSlotBytes);  // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 2 * BN * 4);
+  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (CG=2: the leader's copy is used)
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA          (every CTA's own copy)
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue     (every CTA's own copy)
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA     (CG=2: the leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader
+  if ((smem_u32(smem) & 1023u) != 0) __trap();             // swizzled tiles need 1024-byte alignment
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA in the group
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_units = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
     int stage = 0;
     uint32_t phase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    for (int unit = unit0; unit < num_units; unit += unit_stride) {
       const int tile = unit / p.split_k, split = unit % p.split_k;
-      const int m0 = (tile / p.num_n_tiles) * kBM, n0 = (tile % p.num_n_tiles) * BN;
+      const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * BNL;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -95,20 +144,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           uint8_t* sB = sA + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::kStageBytes);
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_pair(tm, &full_bar[stage], dst, c0, c1);
+            else tma_load_2d(tm, &full_bar[stage], dst, c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(&tmA, &full_bar[stage], sA, kb * kBK, m0);  // box {64 k, 128 rows}
+            load(&tmA, sA, kb * kBK, m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < kBM / 64; ++j)  // box {64 m, 64 k-rows} per 64-wide M block
-              tma_load_2d(&tmA, &full_bar[stage], sA + j * 8192, m0 + j * 64, kb * kBK);
+            for (int j = 0; j < kBM / 64; ++j) load(&tmA, sA + j * 8192, m0 + j * 64, kb * kBK);  // box {64 m, 64 k}
           }
           if constexpr (!B_MN) {
-            tma_load_2d(&tmB, &full_bar[stage], sB, kb * kBK, n0);  // box {64 k, BN rows}
+            load(&tmB, sB, kb * kBK, n0);  // box {64 k, BNL rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&tmB, &full_bar[stage], sB + j * 8192, n0 + j * 64, kb * kBK);
+            for (int j = 0; j < BNL / 64; ++j) load(&tmB, sB + j * 8192, n0 + j * 64, kb * kBK);
           }
         }
         __syncwarp();
@@ -116,137 +167,200 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    constexpr uint32_t idesc = umma_idesc(/*bf16*/ 1, A_MN ? 1 : 0, B_MN ? 1 : 0, kBM, BN);
-    // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major SW128: 64-wide MN blocks
-    // 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
-    constexpr uint64_t descA = A_MN ? smem_desc_sw128(8192, 1024) : smem_desc_sw128(16, 1024);
-    constexpr uint64_t descB = B_MN ? smem_desc_sw128(8192, 1024) : smem_desc_sw128(16, 1024);
-    constexpr uint32_t kStepA = A_MN ? kUmmaK * 128 : kUmmaK * 2;  // bytes per 16-wide K step
-    constexpr uint32_t kStepB = B_MN ? kUmmaK * 128 : kUmmaK * 2;
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int split = unit % p.split_k;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ============================== MMA issuer (leader CTA only when CG = 2) ==============================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(/*bf16*/ 1, A_MN ? 1 : 0, B_MN ? 1 : 0, kBM * CG, BN);
+      // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major SW128: 64-wide MN blocks
+      // 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+      constexpr uint64_t descA = A_MN ? smem_desc_sw128(8192, 1024) : smem_desc_sw128(16, 1024);
+      constexpr uint64_t descB = B_MN ? smem_desc_sw128(8192, 1024) : smem_desc_sw128(16, 1024);
+      constexpr uint32_t kStepA = A_MN ? kUmmaK * 128 : kUmmaK * 2;  // bytes per 16-wide K step
+      constexpr uint32_t kStepB = B_MN ? kUmmaK * 128 : kUmmaK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int split = unit % p.split_k;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // every epilogue warp has drained this accumulator
         tc_fence_after_sync();
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sB = sA + Cfg::kABytes;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sB = sA + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            umma_f16(d_tmem, smem_desc_addr(descA, sA + k * kStepA), smem_desc_addr(descB, sB + k * kStepB), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t da = smem_desc_addr(descA, sA + k * kStepA), db = smem_desc_addr(descB, sB + k * kStepB);
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if constexpr (CG == 2) umma_f16_pair(d_tmem, da, db, idesc, accum);
+              else umma_f16(d_tmem, da, db, idesc, accum);
+            }
+            if constexpr (CG == 2) {
+              umma_commit_pair(&empty_bar[stage], 3);                    // smem slot free in both CTAs
+              if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc], 3);   // accumulator complete in both CTAs
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            }
           }
-          umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ============================== epilogue (warps 2..9) ==============================
     const avt_epilogue_t& ep = p.ep;
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
-    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp handles
+    const int ew = warp - 2;
+    const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the only ones this warp may read
+    const int chalf = ew >> 2;      // which half of the tile's columns this warp handles
+    const int etid = threadIdx.x - 64;
+    uint8_t* my_slots = sStageOut + ew * 2 * kSlotBytes;
+    uint32_t n_st = 0;              // TMA stores issued by this warp (slot = n_st & 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    const bool scale_acc = ep.alpha != 1.0f;
+
+    auto tma_store_chunk = [&](const CUtensorMap* tm, const float* v, int col0, int row0) {
+      uint8_t* slot = my_slots + (n_st & 1) * kSlotBytes;
+      if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago no longer reads this slot
+      __syncwarp();
+      const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte offset
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ sw) << 4)) = pack8(v + 8 * j);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tm, slot, col0, row0);
+        tma_store_commit();
+      }
+      ++n_st;
+    };
+
+    for (int unit = unit0; unit < num_units; unit += unit_stride) {
       const int tile = unit / p.split_k;
-      const int m0 = (tile / p.num_n_tiles) * kBM, n0 = (tile % p.num_n_tiles) * BN;
-      const int row = m0 + quarter * 32 + lane;
+      const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int row0 = m0 + quarter * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
+      // stage this tile's bias slice in smem (one global read per column instead of one per row)
+      float* bias_s = sBias + acc * BN;
+      if (ep.bias) {
+        for (int i = etid; i < BN; i += 32 * kEpiWarps) bias_s[i] = (n0 + i < p.N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
       const int pos_t = ep.pos_period > 0 ? row % ep.pos_period : 0;
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) break;  // N is a multiple of 32 (checked on host): whole chunks only
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c0, r);
+        // independent global loads are issued before waiting for the TMEM load
+        uint4 zraw[4];
+        if (ep.dact_z && row_ok) {
+          const uint4* zp =
+              reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zraw[j] = __ldg(zp + j);
+        }
         tmem_ld_wait();
-        const int col0 = n0 + c0;
-        if (row_ok && col0 < p.N) {  // N is a multiple of 32 on every path that reaches here (checked on host)
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-          if (ep.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (scale_acc) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+        }
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.pos_period > 0 && row_ok) {
+          if (pos_t == 0 && ep.cls) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col0 + j));
+              v[j] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w;
             }
           }
-          if (ep.pos_period > 0) {
-            if (pos_t == 0 && ep.cls) {
+          const float* pp = ep.pos + (size_t)pos_t * p.N + col0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col0 + j));
-                v[j] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w;
-              }
-            }
-            const float* pp = ep.pos + (size_t)pos_t * p.N + col0;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pp + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.aux_z) {
+          float a[32];
+          if (ep.aux_mode == 1) {  // save act'(pre-activation): backward then only multiplies
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(pp + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            for (int j = 0; j < 32; ++j) act_and_grad(ep.act, v[j], v[j], a[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              a[j] = v[j];
+              v[j] = apply_act(ep.act, v[j]);
             }
           }
-          if (ep.aux_z) {
+          if (p.tma_out) {
+            tma_store_chunk(&tmAux, a, col0, row0);
+          } else if (row_ok) {
             uint4* zp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              zp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 8 * j);
           }
-          if (ep.act != AVT_ACT_NONE) {
+        } else if (ep.act != AVT_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(ep.act, v[j]);
-          }
-          if (ep.dact_z) {
-            const uint4* zp =
-                reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col0);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(ep.act, v[j]);
+        }
+        if (ep.dact_z && row_ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 z = __ldg(zp + j);
-              const uint32_t zz[4] = {z.x, z.y, z.z, z.w};
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t zz[4] = {zraw[j].x, zraw[j].y, zraw[j].z, zraw[j].w};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[8 * j + 2 * q] *= apply_act_grad(ep.dact, bf16_lo(zz[q]));
-                v[8 * j + 2 * q + 1] *= apply_act_grad(ep.dact, bf16_hi(zz[q]));
-              }
+            for (int q = 0; q < 4; ++q) {
+              const float z0 = bf16_lo(zz[q]), z1 = bf16_hi(zz[q]);
+              v[8 * j + 2 * q] *= ep.dact_mode == 1 ? z0 : apply_act_grad(ep.dact, z0);
+              v[8 * j + 2 * q + 1] *= ep.dact_mode == 1 ? z1 : apply_act_grad(ep.dact, z1);
             }
           }
-          if (ep.drop_p > 0.f) {
-            const uint64_t g0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)col0) >> 2;
+        }
+        if (ep.drop_p > 0.f) {
+          const uint64_t g0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)col0) >> 2;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t keep = dropout_keep4(ep.drop_seed, ep.drop_offset, g0 + j, ep.drop_p);
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t keep = dropout_keep4(ep.drop_seed, ep.drop_offset, g0 + j, ep.drop_p);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) v[4 * j + q] = ((keep >> q) & 1u) ? v[4 * j + q] * keep_scale : 0.f;
-            }
+            for (int q = 0; q < 4; ++q) v[4 * j + q] = ((keep >> q) & 1u) ? v[4 * j + q] * keep_scale : 0.f;
           }
-          if (ep.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col0);
+        }
+        if (ep.residual && row_ok) {
+          const float4* rp = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(rp + j);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(rp + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
+        }
+        if (p.tma_out) {
+          tma_store_chunk(&tmOut, v, col0, row0);
+        } else if (row_ok) {
           if (ep.out_fp32) {
             float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
             if (p.split_k > 1) {
@@ -268,23 +382,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
           }
         }
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's barrier collects both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait<0>();  // all staged results have reached global memory
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA frees TMEM / exits while its peer still uses the pair
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -305,9 +425,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; 128B swizzle.
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; swizzle_bytes in {64, 128}.
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                      uint32_t box_outer) {
+                      uint32_t box_outer, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled", "driver entry point not available", __FILE__, __LINE__);
@@ -318,8 +438,8 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof msg, "CUresult %d (base %p inner %llu outer %llu ld %llu box %u x %u)", (int)r, base,
@@ -330,29 +450,44 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return AVT_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+struct GemmMaps {
+  CUtensorMap a, b, out, aux;
+};
+
+template <int BN, int CG, bool A_MN, bool B_MN>
+static int launch_gemm(const GemmMaps& tm, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_bf16_kernel<BN, CG, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     AVT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int units = p.num_m_tiles * p.num_n_tiles * p.split_k;
-  const int grid = units < num_sms() ? units : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
-  AVT_CUDA_OK(cudaGetLastError());
+  const int groups = num_sms() / CG;
+  const int grid = CG * (units < groups ? units : groups);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AVT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, p));
   return AVT_OK;
 }
 
-template <int BN>
-static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                          cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, p, s);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, p, s);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, p, s);
-  return launch_gemm<BN, true, true>(tmA, tmB, p, s);
+template <int BN, int CG>
+static int dispatch_major(int a_mn, int b_mn, const GemmMaps& tm, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, CG, false, false>(tm, p, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, CG, false, true>(tm, p, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, CG, true, false>(tm, p, s);
+  return launch_gemm<BN, CG, true, true>(tm, p, s);
 }
 
 }  // namespace avt
@@ -360,7 +495,8 @@ static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUte
 using namespace avt;
 
 extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M,
-                             int64_t N, int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, void* stream) {
+                             int64_t N, int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group,
+                             void* stream) {
   AVT_REQUIRE(A && B && ep && ep->out, "null pointer");
   AVT_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
   AVT_REQUIRE(N % 32 == 0, "N must be a multiple of 32");
@@ -368,8 +504,10 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   AVT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
               "operands must be 16-byte aligned");
   AVT_REQUIRE(ep->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0, "output must be 16-byte aligned");
+  if (cta_group != 1 && cta_group != 2) cta_group = (M >= 1024 && N >= 256) ? 2 : 1;  // pairs pay off on big tiles
   if (block_n <= 0) block_n = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   AVT_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 64, 128 or 256");
+  if (cta_group == 2 && block_n == 64) cta_group = 1;
   if (split_k < 1) split_k = 1;
   if (split_k > 1) {
     AVT_REQUIRE(ep->out_fp32 && !ep->bias && !ep->aux_z && !ep->dact_z && !ep->residual && ep->act == AVT_ACT_NONE &&
@@ -381,7 +519,7 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
 
   GemmParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.num_m_tiles = (int)((M + kBM - 1) / kBM);
+  p.num_m_tiles = (int)((M + kBM * cta_group - 1) / (kBM * cta_group));
   p.num_n_tiles = (int)((N + block_n - 1) / block_n);
   p.num_k_blocks = (int)((K + kBK - 1) / kBK);
   if (split_k > p.num_k_blocks) split_k = p.num_k_blocks;
@@ -389,20 +527,33 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.ep = *ep;
   if (p.ep.alpha == 0.f) p.ep.alpha = 1.0f;
+  p.tma_out = (!ep->out_fp32 && p.split_k == 1) ? 1 : 0;
 
-  CUtensorMap tmA, tmB;
+  GemmMaps tm;
   int rc;
-  if (!a_mn) rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
-  else       rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK);
+  const uint32_t bnl = (uint32_t)(block_n / cta_group);
+  if (!a_mn) rc = make_tmap_bf16_2d(&tm.a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM, 128);
+  else       rc = make_tmap_bf16_2d(&tm.a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK, 128);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, (uint32_t)block_n);
-  else       rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
+  if (!b_mn) rc = make_tmap_bf16_2d(&tm.b, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, bnl, 128);
+  else       rc = make_tmap_bf16_2d(&tm.b, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK, 128);
   if (rc) return rc;
+  tm.out = tm.a;
+  tm.aux = tm.a;
+  if (p.tma_out) {
+    if ((rc = make_tmap_bf16_2d(&tm.out, ep->out, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldo, 32, 32, 64))) return rc;
+    if (ep->aux_z && (rc = make_tmap_bf16_2d(&tm.aux, ep->aux_z, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldz, 32, 32, 64)))
+      return rc;
+  }
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cta_group == 2) {
+    if (block_n == 128) return dispatch_major<128, 2>(a_mn, b_mn, tm, p, s);
+    return dispatch_major<256, 2>(a_mn, b_mn, tm, p, s);
+  }
   switch (block_n) {
-    case 64: return dispatch_major<64>(a_mn, b_mn, tmA, tmB, p, s);
-    case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, p, s);
-    default: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, p, s);
+    case 64: return dispatch_major<64, 1>(a_mn, b_mn, tm, p, s);
+    case 128: return dispatch_major<128, 1>(a_mn, b_mn, tm, p, s);
+    default: return dispatch_major<256, 1>(a_mn, b_mn, tm, p, s);
   }
 }

@@ -14,7 +14,8 @@ constexpr int kLnWarps = 8;
 // VPT = float4 vectors per lane; covers D <= VPT*128 (columns >= D are masked).
 template <int VPT>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
+ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const bf16* __restrict__ add, int64_t add_stride,
+              float* __restrict__ x_out, int64_t xo_stride, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, int64_t rows, int D, void* __restrict__ y, int y_fp32,
               int64_t y_stride, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   const int lane = threadIdx.x & 31;
@@ -29,6 +30,11 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
     for (int i = 0; i < VPT; ++i) {
       const int c = (i * 32 + lane) * 4;
       v[i] = c < D ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add && c < D) {  // residual stream update fused in: x_new = x + branch (bf16), x_new is what gets normalised
+        const uint2 a = *reinterpret_cast<const uint2*>(add + r * add_stride + c);
+        v[i].x += bf16_lo(a.x); v[i].y += bf16_hi(a.x); v[i].z += bf16_lo(a.y); v[i].w += bf16_hi(a.y);
+        if (x_out) *reinterpret_cast<float4*>(x_out + r * xo_stride + c) = v[i];
+      }
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
     const float mean = warp_sum(s) * inv_d;
@@ -168,12 +174,13 @@ ln_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int D, 
 }
 
 template <int VPT>
-static int launch_fwd(const float* x, int64_t xs, const float* g, const float* b, float eps, int64_t rows, int D, void* y,
-                      int y_fp32, int64_t ys, float* mean, float* rstd, cudaStream_t st) {
+static int launch_fwd(const float* x, int64_t xs, const bf16* add, int64_t as, float* xo, int64_t xos, const float* g,
+                      const float* b, float eps, int64_t rows, int D, void* y, int y_fp32, int64_t ys, float* mean,
+                      float* rstd, cudaStream_t st) {
   int64_t blocks = (rows + kLnWarps - 1) / kLnWarps;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  ln_fwd_kernel<VPT><<<(int)blocks, kLnWarps * 32, 0, st>>>(x, xs, g, b, eps, rows, D, y, y_fp32, ys, mean, rstd);
+  ln_fwd_kernel<VPT><<<(int)blocks, kLnWarps * 32, 0, st>>>(x, xs, add, as, xo, xos, g, b, eps, rows, D, y, y_fp32, ys, mean, rstd);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
@@ -198,15 +205,17 @@ using namespace avt;
     else { constexpr int V = 16; CALL; }               \
   } while (0)
 
-extern "C" int avt_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta, float eps,
-                                 int64_t rows, int D, void* y, int y_fp32, int64_t y_stride, float* mean, float* rstd,
-                                 void* stream) {
+extern "C" int avt_layernorm_fwd(const float* x, int64_t x_stride, const void* add_bf16, int64_t add_stride, float* x_out,
+                                 int64_t x_out_stride, const float* gamma, const float* beta, float eps, int64_t rows,
+                                 int D, void* y, int y_fp32, int64_t y_stride, float* mean, float* rstd, void* stream) {
   AVT_REQUIRE(x && gamma && beta && y, "null pointer");
   AVT_REQUIRE(D > 0 && D <= 2048 && D % 4 == 0, "D must be a multiple of 4 and <= 2048");
-  AVT_REQUIRE(x_stride % 4 == 0 && y_stride % 4 == 0, "row strides must be multiples of 4");
+  AVT_REQUIRE(x_stride % 4 == 0 && y_stride % 4 == 0 && add_stride % 4 == 0 && x_out_stride % 4 == 0,
+              "row strides must be multiples of 4");
   if (rows <= 0) return AVT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  AVT_LN_DISPATCH(D, return launch_fwd<V>(x, x_stride, gamma, beta, eps, rows, D, y, y_fp32, y_stride, mean, rstd, st));
+  AVT_LN_DISPATCH(D, return launch_fwd<V>(x, x_stride, reinterpret_cast<const bf16*>(add_bf16), add_stride, x_out,
+                                          x_out_stride, gamma, beta, eps, rows, D, y, y_fp32, y_stride, mean, rstd, st));
   return AVT_OK;
 }
 

@@ -182,6 +182,7 @@ class BlockStack:
             "ln2": [e(M, D) for _ in range(nl)], "z": [e(M, 4 * D) for _ in range(nl)],
             "h": [e(M, 4 * D) for _ in range(nl)],
             "st": [e(4, M, dt=f32) for _ in range(nl)],           # mean1, rstd1, mean2, rstd2
+            "y": e(M, D),                                          # branch output (attention / MLP), bf16
         }
         if train:
             w.update({"dx": e(M, D, dt=f32), "dxb": e(M, D), "dz": e(M, 4 * D), "dln": e(M, D), "datt": e(M, D),
@@ -198,10 +199,11 @@ class BlockStack:
 
     @staticmethod
     def _xbuf(w, train, k):
-        return w["x"][k] if train else w["x"][k % 3]
+        return w["x"][max(k, 0)] if train else w["x"][k % 3]
 
     def forward(self, w, nb, ntok, train, rng=(0, 0), dropout=False):
-        """Runs all blocks on w["x"][0]; returns the fp32 residual stream after the last block.
+        """Runs all blocks on w["x"][0]. The last residual add is left pending so the caller can fuse it into its
+        final LayerNorm: returns (x_mid_last fp32, y_last bf16) with stack output = x_mid_last + y_last.
         train: keep every layer's activations for backward. dropout: apply spec.p_attn / p_resid."""
         s, pk = self.s, self.pack
         D = s.dim
@@ -210,24 +212,31 @@ class BlockStack:
         seed, off = rng
         p_attn = s.p_attn if dropout else 0.0
         p_res = s.p_resid if dropout else 0.0
+        y = w["y"]
         for i in range(s.layers):
             j = i if train else 0
             nm = {k: v.format(i=i) for k, v in s.names.items()}
             st = w["st"][j]
-            xin, xmid, xout = (self._xbuf(w, train, 2 * i + k) for k in range(3))
-            ops.layernorm_fwd(xin, pk.wv(nm["ln1"] + ".weight"), pk.wv(nm["ln1"] + ".bias"), s.eps, w["ln1"][j], st[0], st[1])
+            xprev, xin, xmid = (self._xbuf(w, train, 2 * i + k) for k in (-1, 0, 1))
+            g1, b1 = pk.wv(nm["ln1"] + ".weight"), pk.wv(nm["ln1"] + ".bias")
+            if i == 0:
+                ops.layernorm_fwd(xin, g1, b1, s.eps, w["ln1"][j], st[0], st[1])
+            else:   # x_in = x_mid(prev) + mlp branch(prev), fused with this layer's LN1
+                ops.layernorm_fwd(xprev, g1, b1, s.eps, w["ln1"][j], st[0], st[1], add=y, x_out=xin)
             self._fwd(w["ln1"][j], nm["qkv"] + ".weight", w["qkv"][j], bias=pk.wv(nm["qkv"] + ".bias"))
             self._attn_fwd(w["qkv"][j], w["att"][j], w["lse"][j], nb, ntok, hd, scale, p_attn, seed, off + (4 * i << 28))
-            self._fwd(w["att"][j], nm["proj"] + ".weight", xmid, bias=pk.wv(nm["proj"] + ".bias"), residual=xin,
+            self._fwd(w["att"][j], nm["proj"] + ".weight", y, bias=pk.wv(nm["proj"] + ".bias"),
                       drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 1) << 28))
-            ops.layernorm_fwd(xmid, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3])
+            ops.layernorm_fwd(xin, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3],
+                              add=y, x_out=xmid)
+            # fc1 epilogue writes gelu(z) and gelu'(z): backward only multiplies
             self._fwd(w["ln2"][j], nm["fc1"] + ".weight", w["h"][j], bias=pk.wv(nm["fc1"] + ".bias"), act=s.act,
-                      aux_z=w["z"][j] if train else None)
-            self._fwd(w["h"][j], nm["fc2"] + ".weight", xout, bias=pk.wv(nm["fc2"] + ".bias"), residual=xmid,
+                      aux_z=w["z"][j] if train else None, aux_grad=True)
+            self._fwd(w["h"][j], nm["fc2"] + ".weight", y, bias=pk.wv(nm["fc2"] + ".bias"),
                       drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 2) << 28))
         w["rng"] = (seed, off, p_attn, p_res)
         w["dims"] = (nb, ntok)
-        return self._xbuf(w, train, 2 * s.layers)
+        return self._xbuf(w, train, 2 * s.layers - 1), y
 
     def _attn_fwd(self, qkv, out, lse, nb, ntok, hd, scale, p, seed, off):
         s = self.s
@@ -267,7 +276,7 @@ class BlockStack:
                 g = w["g"]
                 ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 2) << 28), y_bf16=g)
             self._wgrad(w["h"][i], g, nm["fc2"] + ".weight", nm["fc2"] + ".bias")
-            self._dgrad(g, nm["fc2"] + ".weight", w["dz"], dact_z=w["z"][i], dact=s.act)
+            self._dgrad(g, nm["fc2"] + ".weight", w["dz"], dact_z=w["z"][i], dact=s.act, dact_is_grad=True)
             self._wgrad(w["ln2"][i], w["dz"], nm["fc1"] + ".weight", nm["fc1"] + ".bias")
             self._dgrad(w["dz"], nm["fc1"] + ".weight", w["dln"])
             ops.layernorm_bwd(w["dln"], xmid, st[2], st[3], pk.wv(nm["ln2"] + ".weight"), dx,

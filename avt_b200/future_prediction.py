@@ -186,9 +186,10 @@ class AVTh(nn.Module):
         # h0 = dropout(encoder(feats) + wpe[0:T])   (reference :163 + HF GPT2Model.forward)
         ops.gemm(a["xb"], pk.bv("encoder.weight"), w["x"][0], pos=pk.wv("gpt_model.wpe.weight")[:T], pos_period=T,
                  drop_p=p_embd, drop_seed=seed, drop_offset=off + (255 << 28))
-        xf = st.forward(w, B, T, train_graph, rng=(seed, off), dropout=drop)
-        ops.layernorm_fwd(xf, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, a["lnf"],
-                          a["fst"][0], a["fst"][1])
+        xmid, y = st.forward(w, B, T, train_graph, rng=(seed, off), dropout=drop)
+        xf = st._xbuf(w, train_graph, 2 * self.n_layer)
+        ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, a["lnf"],
+                          a["fst"][0], a["fst"][1], add=y, x_out=xf)
         decoded = torch.empty(M, C, dtype=torch.float32, device=dev)
         ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded)
         return decoded, (w, xf, B, T, p_embd, seed, off)

@@ -25,8 +25,8 @@ def _chk_cuda(*ts):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, aux_z=None, dact_z=None,
-         dact=ACT_NONE, pos=None, cls=None, pos_period=0, alpha=1.0, drop_p=0.0, drop_seed=0, drop_offset=0,
-         accumulate=False, split_k=1, block_n=0):
+         dact=ACT_NONE, aux_grad=False, dact_is_grad=False, pos=None, cls=None, pos_period=0, alpha=1.0, drop_p=0.0,
+         drop_seed=0, drop_offset=0, accumulate=False, split_k=1, block_n=0, cta_group=0):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_mn/b_mn: operand is stored transposed ([K,M] / [K,N])."""
     _chk_cuda(a, b, out, bias, residual, aux_z, dact_z, pos, cls)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -57,6 +57,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
     ep.pos_period = pos_period
     ep.act = act
     ep.dact = dact
+    ep.aux_mode = 1 if aux_grad else 0
+    ep.dact_mode = 1 if dact_is_grad else 0
     ep.alpha = alpha
     ep.drop_p = drop_p
     ep.drop_seed = drop_seed
@@ -68,18 +70,27 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
         assert out.dtype == torch.bfloat16
     ep.accumulate = 1 if accumulate else 0
     _lib.call("avt_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
-              C.byref(ep), split_k, block_n, _stream())
+              C.byref(ep), split_k, block_n, cta_group, _stream())
     return out
 
 
-def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, rows=None, x_stride=None):
-    """y = LN(x) (x fp32 [rows, D] with row stride x_stride; y bf16 or fp32 [rows, D])."""
-    _chk_cuda(x, gamma, beta, y)
+def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, rows=None, x_stride=None, add=None, add_stride=None,
+                  x_out=None, x_out_stride=None):
+    """y = LN(x [+ add]) (x fp32 [rows, D] with row stride x_stride; add bf16 branch output; x_out fp32 receives
+    x + add; y bf16 or fp32 [rows, D])."""
+    _chk_cuda(x, gamma, beta, y, add, x_out)
     D = gamma.numel()
     rows = y.shape[0] if rows is None else rows
     x_stride = x.stride(0) if x_stride is None else x_stride
-    _lib.call("avt_layernorm_fwd", _ptr(x), x_stride, _ptr(gamma), _ptr(beta), float(eps), rows, D, _ptr(y),
-              int(y.dtype == torch.float32), y.stride(0), _ptr(mean), _ptr(rstd), _stream())
+    if add is not None:
+        assert add.dtype == torch.bfloat16
+        add_stride = add.stride(0) if add_stride is None else add_stride
+    if x_out is not None:
+        assert x_out.dtype == torch.float32 and add is not None
+        x_out_stride = x_out.stride(0) if x_out_stride is None else x_out_stride
+    _lib.call("avt_layernorm_fwd", _ptr(x), x_stride, _ptr(add), add_stride or 0, _ptr(x_out), x_out_stride or 0, _ptr(gamma),
+              _ptr(beta), float(eps), rows, D, _ptr(y), int(y.dtype == torch.float32), y.stride(0), _ptr(mean), _ptr(rstd),
+              _stream())
     return y
 
 

@@ -40,9 +40,11 @@ int avt_check_device(void);
  *   v = alpha * acc
  *   v += bias[c]
  *   if pos_period > 0:  t = r % pos_period;  if (t == 0 && cls) v = cls[c];  v += pos[t * N + c]
- *   if aux_z:   aux_z[r * ldz + c] = bf16(v)              (pre-activation, saved for backward)
+ *   if aux_z:   aux_z[r * ldz + c] = bf16(aux_mode == 1 ? act'(v) : v)      (saved for backward)
  *   v = act(v)
- *   if dact_z:  v *= dact'(dact_z[r * ldz + c])           (backward through activation kind `dact`)
+ *   if dact_z:  v *= (dact_mode == 1 ? dact_z[r * ldz + c] : dact'(dact_z[r * ldz + c]))
+ *               (backward through the activation: dact_z holds either the pre-activation, differentiated here
+ *                with kind `dact`, or the derivative itself as saved by a forward with aux_mode = 1)
  *   if drop_p > 0: v = keep(seed, drop_offset, r * N + c) ? v / (1 - drop_p) : 0
  *   if residual: v += residual[r * ldr + c]
  *   out[r * ldo + c] = out_fp32 ? v : bf16(v)
@@ -59,6 +61,8 @@ typedef struct avt_epilogue {
   int32_t pos_period;
   int32_t act;
   int32_t dact;
+  int32_t aux_mode;
+  int32_t dact_mode;
   float alpha;
   float drop_p;
   uint64_t drop_seed;
@@ -70,22 +74,27 @@ typedef struct avt_epilogue {
 } avt_epilogue_t;
 
 /* C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 operands, fp32 accumulation in tensor memory
- * (tcgen05.mma, TMA-fed 128B-swizzled smem ring, persistent tile loop).
+ * (tcgen05.mma, TMA-fed 128B-swizzled smem ring, persistent tile loop). block_n in {0 = auto, 64, 128, 256};
+ * cta_group in {0 = auto, 1, 2}: 2 runs CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles) for large problems.
  *   a_mn = 0: A stored [M rows][K cols] (ld = lda);  a_mn = 1: A stored transposed, [K rows][M cols].
  *   b_mn = 0: B stored [N rows][K cols] (ld = ldb);  b_mn = 1: B stored transposed, [K rows][N cols].
  * Replaces torch.nn.Linear / F.linear (timm Attention.qkv/proj, Mlp.fc1/fc2; reference
  * models/future_prediction.py:80-81 encoder/decoder), HF Conv1D (torch.addmm; GPT2Attention.c_attn /
  * c_proj, GPT2MLP.c_fc / c_proj) and their autograd dgrad / wgrad matmuls (func/train.py:222). */
 int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
-                  int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, void* stream);
+                  int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group, void* stream);
 
-/* y[r,:] = LayerNorm(x[r,:]) * gamma + beta over the last dim D (<= 2048, multiple of 4); one warp per row.
+/* y[r,:] = LayerNorm(x'[r,:]) * gamma + beta over the last dim D (<= 2048, multiple of 4); one warp per row.
+ * x' = x, or — residual update fused in — x' = x + add_bf16 (a bf16 branch output), with x' also written to
+ * x_out (fp32, may be NULL): `x = x + drop_path(attn(...))` / `x = x + mlp(...)` of timm Block.forward and the
+ * two residual adds of HF GPT2Block.forward happen here instead of in a GEMM epilogue, in coalesced rows.
  * x fp32 with row stride x_stride (elements) — a stride of tokens*D selects one token per frame (the CLS
  * row for timm VisionTransformer.norm + x[:, 0]). y is bf16 (y_fp32 = 0) or fp32. mean / rstd ([rows],
  * may be NULL) are saved for backward. Replaces torch.nn.LayerNorm in timm Block.norm1/norm2,
  * VisionTransformer.norm (eps 1e-6) and HF GPT2Block.ln_1/ln_2, GPT2Model.ln_f (eps 1e-5). */
-int avt_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta, float eps, int64_t rows,
-                      int D, void* y, int y_fp32, int64_t y_stride, float* mean, float* rstd, void* stream);
+int avt_layernorm_fwd(const float* x, int64_t x_stride, const void* add_bf16, int64_t add_stride, float* x_out,
+                      int64_t x_out_stride, const float* gamma, const float* beta, float eps, int64_t rows, int D, void* y,
+                      int y_fp32, int64_t y_stride, float* mean, float* rstd, void* stream);
 
 /* LayerNorm backward. dx_out = (dx_in ? dx_in : 0) + dLN(dy); optional bf16 copy of dx_out (the A operand
  * of the next dgrad / wgrad GEMM); dgamma / dbeta are overwritten or accumulated. `workspace` must hold

@@ -42,11 +42,14 @@ def _check(out, ref, what=""):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("M,N,K,bn", [
-    (128, 256, 64, 256), (128, 64, 64, 64), (256, 512, 256, 256), (384, 384, 192, 128),
-    (200, 768, 768, 256), (80, 2048, 768, 64), (1000, 1024, 80, 128), (15760, 768, 768, 256),
+@pytest.mark.parametrize("M,N,K,bn,cg", [
+    (128, 256, 64, 256, 1), (128, 64, 64, 64, 1), (256, 512, 256, 256, 1), (384, 384, 192, 128, 1),
+    (200, 768, 768, 256, 1), (80, 2048, 768, 64, 1), (1000, 1024, 80, 128, 1), (15760, 768, 768, 256, 1),
+    # CTA pairs (tcgen05 cta_group::2): 256-row pair tiles, ragged M, both block widths
+    (256, 256, 64, 256, 2), (512, 512, 256, 256, 2), (200, 768, 768, 256, 2), (1000, 1024, 80, 128, 2),
+    (384, 384, 192, 128, 2), (15760, 768, 768, 256, 2), (15760, 2304, 768, 256, 2),
 ])
-def test_gemm_layouts(a_mn, b_mn, M, N, K, bn):
+def test_gemm_layouts(a_mn, b_mn, M, N, K, bn, cg):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     a = _mk((K, M) if a_mn else (M, K), g)
@@ -55,9 +58,9 @@ def test_gemm_layouts(a_mn, b_mn, M, N, K, bn):
         pytest.skip("transposed A needs M % 8 == 0 (16-byte row pitch)")
     for dt in (torch.float32, torch.bfloat16):
         out = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
-        ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+        ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, block_n=bn, cta_group=cg)
         torch.cuda.synchronize()
-        _check(out, _ref(a, b, a_mn, b_mn), f"M{M} N{N} K{K} bn{bn} a_mn{a_mn} b_mn{b_mn} {dt}")
+        _check(out, _ref(a, b, a_mn, b_mn), f"M{M} N{N} K{K} bn{bn} cg{cg} a_mn{a_mn} b_mn{b_mn} {dt}")
 
 
 def _gelu_tanh(x):
@@ -65,20 +68,35 @@ def _gelu_tanh(x):
 
 
 @pytest.mark.parametrize("act", [1, 2])
-def test_gemm_bias_act_aux(act):
+@pytest.mark.parametrize("cg,M", [(1, 300), (2, 1500)])
+@pytest.mark.parametrize("out_dt", [torch.bfloat16, torch.float32])
+def test_gemm_bias_act_aux(act, cg, M, out_dt):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(5)
-    M, N, K = 300, 512, 256
+    N, K = 512, 256
     a, b = _mk((M, K), g), _mk((N, K), g, 0.1)
     bias = torch.randn(N, generator=g, device="cuda")
-    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=out_dt)
     z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, b, out, bias=bias, act=act, aux_z=z)
-    pre = _ref(a, b, False, False) + bias.double()
-    _check(z, pre, "aux_z")
+    ops.gemm(a, b, out, bias=bias, act=act, aux_z=z, cta_group=cg)
+    pre = (_ref(a, b, False, False) + bias.double()).requires_grad_(True)
+    _check(z, pre.detach(), "aux_z")
     want = torch.nn.functional.gelu(pre) if act == 1 else _gelu_tanh(pre)
     err = (out.double() - want).abs()
     assert (err <= want.abs() * 2.0**-7 + 2e-3).all(), err.max().item()
+    if out_dt == torch.float32:     # branch-free erf / tanh formulations: abs error ~1e-6
+        assert err.max().item() < 2e-5 * max(1.0, want.abs().max().item())
+    # aux_mode = 1: the epilogue saves act'(pre-activation) instead
+    ops.gemm(a, b, out, bias=bias, act=act, aux_z=z, aux_grad=True, cta_group=cg)
+    (dwant,) = torch.autograd.grad(want.sum(), pre)
+    derr = (z.double() - dwant).abs()
+    assert (derr <= dwant.abs() * 2.0**-8 + 1e-3).all(), derr.max().item()
+    # ... and a backward GEMM multiplies by it directly (dact_mode = 1)
+    g2 = _mk((M, K), g)
+    dz = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(g2, b, dz, dact_z=z, dact_is_grad=True, cta_group=cg)
+    ref = _ref(g2, b, False, False) * z.double()
+    assert ((dz.double() - ref).norm() / ref.norm()).item() < 1e-5
 
 
 @pytest.mark.parametrize("act", [1, 2])

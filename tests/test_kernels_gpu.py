@@ -66,6 +66,32 @@ def test_layernorm_fwd_bwd(rows, D, eps):
     assert rel(dx2, dx) < 1e-6 and rel(dg2, 2 * dg) < 1e-6 and rel(db2, 2 * db) < 1e-6
 
 
+def test_layernorm_fused_residual_add():
+    """x' = x + bf16 branch; LN(x'); x' written back (timm Block / GPT2Block residual adds)."""
+    ops = _ops()
+    rows, D = 1000, 768
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(rows, D, generator=g, device="cuda")
+    add = torch.randn(rows, D, generator=g, device="cuda").to(torch.bfloat16)
+    gamma, beta = torch.randn(D, generator=g, device="cuda"), torch.randn(D, generator=g, device="cuda")
+    y = torch.empty(rows, D, device="cuda")
+    xo = torch.empty(rows, D, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, gamma, beta, 1e-6, y, mean, rstd, add=add, x_out=xo)
+    xn = x.double() + add.double()
+    assert rel(xo, xn) < 1e-7
+    assert rel(y, torch.nn.functional.layer_norm(xn, (D,), gamma.double(), beta.double(), 1e-6)) < 1e-5
+    # strided variant used for the ViT CLS rows: one row per frame, x_out compact
+    F, ntok = 5, 197
+    xb = torch.randn(F * ntok, D, generator=g, device="cuda")
+    ab = torch.randn(F * ntok, D, generator=g, device="cuda").to(torch.bfloat16)
+    yc, xc = torch.empty(F, D, device="cuda"), torch.empty(F, D, device="cuda")
+    ops.layernorm_fwd(xb, gamma, beta, 1e-6, yc, rows=F, x_stride=ntok * D, add=ab, add_stride=ntok * D, x_out=xc)
+    xn = (xb.double() + ab.double()).view(F, ntok, D)[:, 0]
+    assert rel(xc, xn) < 1e-7
+    assert rel(yc, torch.nn.functional.layer_norm(xn, (D,), gamma.double(), beta.double(), 1e-6)) < 1e-5
+
+
 def test_layernorm_strided_cls_rows():
     ops = _ops()
     F, ntok, D = 5, 197, 768

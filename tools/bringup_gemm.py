@@ -78,18 +78,18 @@ def run_perf():
         ("avth c_fc fwd", 80, 8192, 2048, False, True, 1), ("avth c_proj fwd", 80, 2048, 8192, False, True, 1),
     ]
     for name, m, n, k, a_mn, b_mn, sk in cases:
-        for bn in (256, 128):
+        for bn, cg in ((256, 2), (256, 1), (128, 2)):
             a = torch.randn((k, m) if a_mn else (m, k), device=dev).to(torch.bfloat16)
             b = torch.randn((k, n) if b_mn else (n, k), device=dev).to(torch.bfloat16)
             out = torch.zeros(m, n, device=dev, dtype=torch.float32 if sk > 1 else torch.bfloat16)
             for _ in range(3):
-                ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, split_k=sk, block_n=bn)
+                ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, split_k=sk, block_n=bn, cta_group=cg)
             ts = []
             for _ in range(8):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, split_k=sk, block_n=bn)
+                ops.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, split_k=sk, block_n=bn, cta_group=cg)
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
@@ -111,7 +111,7 @@ def run_perf():
                 tc.append(e0.elapsed_time(e1))
             tc.sort()
             fl = 2.0 * m * n * k
-            print(f"{name:18s} bn{bn} M{m} N{n} K{k}: {t*1e3:8.1f} us {fl/t/1e9:8.1f} TF/s | cuBLAS {tc[2]*1e3:8.1f} us"
+            print(f"{name:18s} bn{bn} cg{cg} M{m} N{n} K{k}: {t*1e3:8.1f} us {fl/t/1e9:8.1f} TF/s | cuBLAS {tc[2]*1e3:8.1f} us"
                   f" {fl/tc[2]/1e9:8.1f} TF/s", flush=True)
 
 
