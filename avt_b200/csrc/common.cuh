@@ -86,6 +86,61 @@ __device__ __forceinline__ float apply_act_grad(int act, float x) {
   return act == AVT_ACT_GELU_ERF ? gelu_erf_grad(x) : (act == AVT_ACT_GELU_TANH ? gelu_tanh_grad(x) : 1.0f);
 }
 
+// ---- packed fp32x2 variants (sm_100 FFMA2 / FMUL2 / FADD2: two lanes of work per issued instruction). The fused GEMM
+// epilogues are issue-bound on 8 warps; evaluating two accumulator columns per instruction halves the FMA-pipe slots.
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 normal_cdf2(float2 x) {
+  const float2 u = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), f2(0.70710678118654752f));
+  float2 p = __ffma2_rn(u, f2(0.0000430638f), f2(0.0002765672f));
+  p = __ffma2_rn(p, u, f2(0.0001520143f));
+  p = __ffma2_rn(p, u, f2(0.0092705272f));
+  p = __ffma2_rn(p, u, f2(0.0422820123f));
+  p = __ffma2_rn(p, u, f2(0.0705230784f));
+  p = __ffma2_rn(p, u, f2(1.0f));
+  p = __fmul2_rn(p, p); p = __fmul2_rn(p, p); p = __fmul2_rn(p, p); p = __fmul2_rn(p, p);
+  const float2 r = make_float2(fast_rcp(p.x), fast_rcp(p.y));
+  const float2 he = __ffma2_rn(r, f2(-0.5f), f2(0.5f));   // 0.5 * erf(|x|/sqrt2)
+  return __fadd2_rn(f2(0.5f), make_float2(copysignf(he.x, x.x), copysignf(he.y, x.y)));
+}
+__device__ __forceinline__ float2 normal_pdf2(float2 x) {
+  const float2 t = __fmul2_rn(__fmul2_rn(x, x), f2(-0.72134752044448170f));
+  return __fmul2_rn(make_float2(fast_ex2(t.x), fast_ex2(t.y)), f2(0.39894228040143268f));
+}
+__device__ __forceinline__ float2 tanh2(float2 u) {
+  const float2 t = __fmul2_rn(u, f2(2.8853900817779268f));
+  const float2 e = make_float2(fast_ex2(fminf(t.x, 80.0f)), fast_ex2(fminf(t.y, 80.0f)));
+  const float2 d = __fadd2_rn(e, f2(1.0f));
+  return __ffma2_rn(make_float2(fast_rcp(d.x), fast_rcp(d.y)), f2(-2.0f), f2(1.0f));
+}
+// y = act(x), dy = act'(x) for two elements
+__device__ __forceinline__ void act_and_grad2(int act, float2 x, float2& y, float2& dy, bool want_grad) {
+  if (act == AVT_ACT_GELU_ERF) {
+    const float2 cdf = normal_cdf2(x);
+    y = __fmul2_rn(x, cdf);
+    if (want_grad) dy = __ffma2_rn(x, normal_pdf2(x), cdf);
+  } else if (act == AVT_ACT_GELU_TANH) {
+    const float2 x2 = __fmul2_rn(x, x);
+    const float2 inner = __fmul2_rn(__ffma2_rn(__fmul2_rn(x2, x), f2(0.044715f), x), f2(0.79788456080286536f));
+    const float2 t = tanh2(inner);
+    const float2 hx = __fmul2_rn(x, f2(0.5f));
+    const float2 tp1 = __fadd2_rn(t, f2(1.0f));
+    y = __fmul2_rn(hx, tp1);
+    if (want_grad) {
+      const float2 du = __ffma2_rn(x2, f2(3.0f * 0.044715f * 0.79788456080286536f), f2(0.79788456080286536f));
+      const float2 omt2 = __ffma2_rn(t, make_float2(-t.x, -t.y), f2(1.0f));
+      dy = __ffma2_rn(__fmul2_rn(hx, omt2), du, __fmul2_rn(tp1, f2(0.5f)));
+    }
+  } else {
+    y = x;
+    if (want_grad) dy = f2(1.0f);
+  }
+}
+__device__ __forceinline__ float2 act_grad2(int act, float2 x) {
+  float2 y, dy;
+  act_and_grad2(act, x, y, dy, true);
+  return dy;
+}
+
 // ----------------------------------------------------------------------------- Philox4x32-10
 // Counter-based RNG: the dropout mask of element i is a pure function of (seed, offset, i), so the
 // backward pass regenerates it instead of storing it.

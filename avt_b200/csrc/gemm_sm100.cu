@@ -38,8 +38,8 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = kEpiWarps * 2 * kSlotBytes + 2 * BN * 4;  // staging slots + bias (double-buffered)
-  static constexpr int kBarBytes = 256;
+  static constexpr int kEpiBytes = kEpiWarps * 4 * kSlotBytes + 2 * BN * 4;  // 2 out + 2 in staging slots per warp, bias x2
+  static constexpr int kBarBytes = 512;
   static constexpr int kMaxStages = (kSmemLimit - kEpiBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator
@@ -51,46 +51,32 @@ struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks, split_k, kb_per_split;
   int tma_out;  // bf16 `out` (and aux_z) leave through TMA stores
+  int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
   avt_epilogue_t ep;
 };
 
-__device__ __forceinline__ void act_and_grad(int act, float x, float& y, float& dy) {
-  if (act == AVT_ACT_GELU_ERF) {
-    const float cdf = normal_cdf(x);
-    const float pdf = 0.39894228040143268f * fast_ex2(-0.72134752044448170f * x * x);
-    y = x * cdf;
-    dy = fmaf(x, pdf, cdf);
-  } else if (act == AVT_ACT_GELU_TANH) {
-    const float x2 = x * x;
-    const float t = fast_tanh(0.79788456080286536f * (x + 0.044715f * x * x2));
-    const float du = 0.79788456080286536f * (1.0f + 3.0f * 0.044715f * x2);
-    y = 0.5f * x * (1.0f + t);
-    dy = 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
-  } else {
-    y = x;
-    dy = 1.0f;
-  }
-}
-
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+__device__ __forceinline__ uint4 pack8(const float2* v) {  // 4 float2 = 8 consecutive columns
+  return make_uint4(pack_bf16x2(v[0].x, v[0].y), pack_bf16x2(v[1].x, v[1].y), pack_bf16x2(v[2].x, v[2].y),
+                    pack_bf16x2(v[3].x, v[3].y));
 }
 
 template <int BN, int CG, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
+                 const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int BNL = BN / CG;  // B rows (N extent) held by this CTA
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sStageOut = smem + Cfg::kStages * Cfg::kStageBytes;            // [kEpiWarps][2][kSlotBytes]
-  float* sBias = reinterpret_cast<float*>(sStageOut + kEpiWarps * 2 * kSlotBytes);  // [2][BN]
+  uint8_t* sStageOut = smem + Cfg::kStages * Cfg::kStageBytes;            // [kEpiWarps][2 out + 2 in][kSlotBytes]
+  float* sBias = reinterpret_cast<float*>(sStageOut + kEpiWarps * 4 * kSlotBytes);  // [2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 2 * BN * 4);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (CG=2: the leader's copy is used)
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA          (every CTA's own copy)
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue     (every CTA's own copy)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA     (CG=2: the leader's copy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tin_bar = tempty_bar + 2;              // [kEpiWarps][2] TMA -> epilogue warp (dact_z staging)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tin_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
+    if (p.tma_in) tma_prefetch_desc(&tmIn);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -109,6 +96,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA in the group
     }
+    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&tin_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -217,25 +205,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ============================== epilogue (warps 2..9) ==============================
+    // Math runs on packed fp32x2 (FFMA2): the fused epilogues are issue-bound, two columns per instruction.
     const avt_epilogue_t& ep = p.ep;
     const int ew = warp - 2;
     const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the only ones this warp may read
     const int chalf = ew >> 2;      // which half of the tile's columns this warp handles
     const int etid = threadIdx.x - 64;
-    uint8_t* my_slots = sStageOut + ew * 2 * kSlotBytes;
-    uint32_t n_st = 0;              // TMA stores issued by this warp (slot = n_st & 1)
+    uint8_t* out_slots = sStageOut + ew * 4 * kSlotBytes;   // [2] staging for TMA stores
+    uint8_t* in_slots = out_slots + 2 * kSlotBytes;         // [2] staging for TMA loads (dact_z)
+    uint64_t* in_bar = tin_bar + ew * 2;
+    uint32_t n_st = 0, n_in_issued = 0, n_in_waited = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
     const bool scale_acc = ep.alpha != 1.0f;
+    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte offset (64 B rows)
 
-    auto tma_store_chunk = [&](const CUtensorMap* tm, const float* v, int col0, int row0) {
-      uint8_t* slot = my_slots + (n_st & 1) * kSlotBytes;
+    auto tma_store_chunk = [&](const CUtensorMap* tm, const float2* v, int col0, int row0) {
+      uint8_t* slot = out_slots + (n_st & 1) * kSlotBytes;
       if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago no longer reads this slot
       __syncwarp();
-      const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte offset
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ sw) << 4)) = pack8(v + 8 * j);
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ sw) << 4)) = pack8(v + 4 * j);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -243,6 +235,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_store_commit();
       }
       ++n_st;
+    };
+    auto issue_in = [&](int col0, int row0) {   // prefetch a 32 x 32 bf16 block of dact_z into a staging slot
+      if (lane == 0) {
+        uint64_t* bar = &in_bar[n_in_issued & 1];
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(bar, kSlotBytes);
+        tma_load_2d(&tmIn, bar, in_slots + (n_in_issued & 1) * kSlotBytes, col0, row0);
+      }
+      ++n_in_issued;
     };
 
     for (int unit = unit0; unit < num_units; unit += unit_stride) {
@@ -252,70 +253,86 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m0 + quarter * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
+      const int c_begin = chalf * (BN / 2);
+      const int c_end = min((chalf + 1) * (BN / 2), p.N - n0);  // N is a multiple of 32 (checked on host)
       // stage this tile's bias slice in smem (one global read per column instead of one per row)
       float* bias_s = sBias + acc * BN;
       if (ep.bias) {
         for (int i = etid; i < BN; i += 32 * kEpiWarps) bias_s[i] = (n0 + i < p.N) ? __ldg(ep.bias + n0 + i) : 0.f;
       }
+      if (p.tma_in && c_begin < c_end) issue_in(n0 + c_begin, row0);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
       const int pos_t = ep.pos_period > 0 ? row % ep.pos_period : 0;
 #pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         const int col0 = n0 + c0;
-        if (col0 >= p.N) break;  // N is a multiple of 32 (checked on host): whole chunks only
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c0, r);
-        // independent global loads are issued before waiting for the TMEM load
         uint4 zraw[4];
-        if (ep.dact_z && row_ok) {
-          const uint4* zp =
-              reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col0);
+        if (ep.dact_z) {
+          if (p.tma_in) {
+            if (c0 + 32 < c_end) issue_in(col0 + 32, row0);
+            const uint32_t sl = n_in_waited & 1;
+            mbar_wait(&in_bar[sl], (n_in_waited >> 1) & 1);
+            const uint8_t* slot = in_slots + sl * kSlotBytes + lane * 64;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) zraw[j] = __ldg(zp + j);
+            for (int j = 0; j < 4; ++j) zraw[j] = *reinterpret_cast<const uint4*>(slot + ((j ^ sw) << 4));
+            __syncwarp();
+            ++n_in_waited;
+          } else if (row_ok) {
+            const uint4* zp =
+                reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zraw[j] = __ldg(zp + j);
+          }
         }
         tmem_ld_wait();
-        float v[32];
+        float2 v[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
         if (scale_acc) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+          for (int j = 0; j < 16; ++j) v[j] = __fmul2_rn(v[j], f2(ep.alpha));
         }
         if (ep.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          for (int j = 0; j < 16; j += 2) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + 2 * j);
+            v[j] = __fadd2_rn(v[j], make_float2(b.x, b.y));
+            v[j + 1] = __fadd2_rn(v[j + 1], make_float2(b.z, b.w));
           }
         }
         if (ep.pos_period > 0 && row_ok) {
           if (pos_t == 0 && ep.cls) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col0 + j));
-              v[j] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w;
+            for (int j = 0; j < 16; j += 2) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col0 + 2 * j));
+              v[j] = make_float2(b.x, b.y);
+              v[j + 1] = make_float2(b.z, b.w);
             }
           }
           const float* pp = ep.pos + (size_t)pos_t * p.N + col0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(pp + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          for (int j = 0; j < 16; j += 2) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pp + 2 * j));
+            v[j] = __fadd2_rn(v[j], make_float2(b.x, b.y));
+            v[j + 1] = __fadd2_rn(v[j + 1], make_float2(b.z, b.w));
           }
         }
         if (ep.aux_z) {
-          float a[32];
+          float2 a[16];
           if (ep.aux_mode == 1) {  // save act'(pre-activation): backward then only multiplies
 #pragma unroll
-            for (int j = 0; j < 32; ++j) act_and_grad(ep.act, v[j], v[j], a[j]);
+            for (int j = 0; j < 16; ++j) act_and_grad2(ep.act, v[j], v[j], a[j], true);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               a[j] = v[j];
-              v[j] = apply_act(ep.act, v[j]);
+              float2 unused;
+              act_and_grad2(ep.act, v[j], v[j], unused, false);
             }
           }
           if (p.tma_out) {
@@ -323,21 +340,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else if (row_ok) {
             uint4* zp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 8 * j);
+            for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 4 * j);
           }
         } else if (ep.act != AVT_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(ep.act, v[j]);
+          for (int j = 0; j < 16; ++j) {
+            float2 unused;
+            act_and_grad2(ep.act, v[j], v[j], unused, false);
+          }
         }
-        if (ep.dact_z && row_ok) {
+        if (ep.dact_z && (row_ok || p.tma_in)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t zz[4] = {zraw[j].x, zraw[j].y, zraw[j].z, zraw[j].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float z0 = bf16_lo(zz[q]), z1 = bf16_hi(zz[q]);
-              v[8 * j + 2 * q] *= ep.dact_mode == 1 ? z0 : apply_act_grad(ep.dact, z0);
-              v[8 * j + 2 * q + 1] *= ep.dact_mode == 1 ? z1 : apply_act_grad(ep.dact, z1);
+              const float2 z2 = make_float2(bf16_lo(zz[q]), bf16_hi(zz[q]));
+              v[4 * j + q] = __fmul2_rn(v[4 * j + q], ep.dact_mode == 1 ? z2 : act_grad2(ep.dact, z2));
             }
           }
         }
@@ -346,8 +365,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t keep = dropout_keep4(ep.drop_seed, ep.drop_offset, g0 + j, ep.drop_p);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[4 * j + q] = ((keep >> q) & 1u) ? v[4 * j + q] * keep_scale : 0.f;
+            v[2 * j].x = (keep & 1u) ? v[2 * j].x * keep_scale : 0.f;
+            v[2 * j].y = (keep & 2u) ? v[2 * j].y * keep_scale : 0.f;
+            v[2 * j + 1].x = (keep & 4u) ? v[2 * j + 1].x * keep_scale : 0.f;
+            v[2 * j + 1].y = (keep & 8u) ? v[2 * j + 1].y * keep_scale : 0.f;
           }
         }
         if (ep.residual && row_ok) {
@@ -355,7 +376,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(rp + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            v[2 * j] = __fadd2_rn(v[2 * j], make_float2(b.x, b.y));
+            v[2 * j + 1] = __fadd2_rn(v[2 * j + 1], make_float2(b.z, b.w));
           }
         }
         if (p.tma_out) {
@@ -365,24 +387,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
             if (p.split_k > 1) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                atomicAdd(reinterpret_cast<float4*>(op + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              for (int j = 0; j < 8; ++j)
+                atomicAdd(reinterpret_cast<float4*>(op + 4 * j), make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y));
             } else if (ep.accumulate) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = *reinterpret_cast<float4*>(op + j);
-                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
-                *reinterpret_cast<float4*>(op + j) = o;
+              for (int j = 0; j < 8; ++j) {
+                float4 o = *reinterpret_cast<float4*>(op + 4 * j);
+                o.x += v[2 * j].x; o.y += v[2 * j].y; o.z += v[2 * j + 1].x; o.w += v[2 * j + 1].y;
+                *reinterpret_cast<float4*>(op + 4 * j) = o;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
             }
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 4 * j);
           }
         }
       }
@@ -451,7 +473,7 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 }
 
 struct GemmMaps {
-  CUtensorMap a, b, out, aux;
+  CUtensorMap a, b, out, aux, in;
 };
 
 template <int BN, int CG, bool A_MN, bool B_MN>
@@ -478,7 +500,7 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p, cudaStream_t str
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AVT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, p));
+  AVT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, tm.in, p));
   return AVT_OK;
 }
 
@@ -504,7 +526,7 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   AVT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
               "operands must be 16-byte aligned");
   AVT_REQUIRE(ep->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0, "output must be 16-byte aligned");
-  if (cta_group != 1 && cta_group != 2) cta_group = (M >= 1024 && N >= 256) ? 2 : 1;  // pairs pay off on big tiles
+  if (cta_group != 1 && cta_group != 2) cta_group = (M >= 512 && N >= 256) ? 2 : 1;  // pairs pay off on big tiles
   if (block_n <= 0) block_n = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   AVT_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 64, 128 or 256");
   if (cta_group == 2 && block_n == 64) cta_group = 1;
@@ -528,6 +550,7 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   p.ep = *ep;
   if (p.ep.alpha == 0.f) p.ep.alpha = 1.0f;
   p.tma_out = (!ep->out_fp32 && p.split_k == 1) ? 1 : 0;
+  p.tma_in = ep->dact_z ? 1 : 0;
 
   GemmMaps tm;
   int rc;
@@ -540,6 +563,8 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   if (rc) return rc;
   tm.out = tm.a;
   tm.aux = tm.a;
+  tm.in = tm.a;
+  if (p.tma_in && (rc = make_tmap_bf16_2d(&tm.in, ep->dact_z, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldz, 32, 32, 64))) return rc;
   if (p.tma_out) {
     if ((rc = make_tmap_bf16_2d(&tm.out, ep->out, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldo, 32, 32, 64))) return rc;
     if (ep->aux_z && (rc = make_tmap_bf16_2d(&tm.aux, ep->aux_z, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldz, 32, 32, 64)))

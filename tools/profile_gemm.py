@@ -20,9 +20,9 @@ g = torch.randn(M, 768, device=dev).to(torch.bfloat16)
 w2 = torch.randn(768, 3072, device=dev).to(torch.bfloat16) * 0.03
 for _ in range(2):
     ops.gemm(a, wq, qkv)                                        # plain
-    ops.gemm(a, w1, h, bias=b1, act=1, aux_z=z)                 # GELU + aux
+    ops.gemm(a, w1, h, bias=b1, act=1, aux_z=z, aux_grad=True)  # GELU + gelu' aux
     ops.gemm(a, wp, xo, residual=res)                           # residual fp32
-    ops.gemm(g, w2, dz, b_mn=True, dact_z=z, dact=1)            # dgrad + dGELU
+    ops.gemm(g, w2, dz, b_mn=True, dact_z=z, dact=1, dact_is_grad=True)  # dgrad * gelu'
     ops.gemm(h, g, torch.zeros(3072, 768, device=dev), a_mn=True, b_mn=True, split_k=4)  # wgrad
 torch.cuda.synchronize()
 print("ok")
