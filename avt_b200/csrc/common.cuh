@@ -112,33 +112,49 @@ __device__ __forceinline__ float2 tanh2(float2 u) {
   const float2 d = __fadd2_rn(e, f2(1.0f));
   return __ffma2_rn(make_float2(fast_rcp(d.x), fast_rcp(d.y)), f2(-2.0f), f2(1.0f));
 }
-// y = act(x), dy = act'(x) for two elements
-__device__ __forceinline__ void act_and_grad2(int act, float2 x, float2& y, float2& dy, bool want_grad) {
-  if (act == AVT_ACT_GELU_ERF) {
+// y = act(x), dy = act'(x) for two elements; ACT and GRAD are compile-time so the unrolled epilogue loops carry no branches
+template <int ACT, bool GRAD>
+__device__ __forceinline__ void act_and_grad2(float2 x, float2& y, float2& dy) {
+  if constexpr (ACT == AVT_ACT_GELU_ERF) {
     const float2 cdf = normal_cdf2(x);
     y = __fmul2_rn(x, cdf);
-    if (want_grad) dy = __ffma2_rn(x, normal_pdf2(x), cdf);
-  } else if (act == AVT_ACT_GELU_TANH) {
+    if constexpr (GRAD) dy = __ffma2_rn(x, normal_pdf2(x), cdf);
+  } else if constexpr (ACT == AVT_ACT_GELU_TANH) {
     const float2 x2 = __fmul2_rn(x, x);
     const float2 inner = __fmul2_rn(__ffma2_rn(__fmul2_rn(x2, x), f2(0.044715f), x), f2(0.79788456080286536f));
     const float2 t = tanh2(inner);
     const float2 hx = __fmul2_rn(x, f2(0.5f));
     const float2 tp1 = __fadd2_rn(t, f2(1.0f));
     y = __fmul2_rn(hx, tp1);
-    if (want_grad) {
+    if constexpr (GRAD) {
       const float2 du = __ffma2_rn(x2, f2(3.0f * 0.044715f * 0.79788456080286536f), f2(0.79788456080286536f));
       const float2 omt2 = __ffma2_rn(t, make_float2(-t.x, -t.y), f2(1.0f));
       dy = __ffma2_rn(__fmul2_rn(hx, omt2), du, __fmul2_rn(tp1, f2(0.5f)));
     }
   } else {
     y = x;
-    if (want_grad) dy = f2(1.0f);
+    if constexpr (GRAD) dy = f2(1.0f);
   }
 }
-__device__ __forceinline__ float2 act_grad2(int act, float2 x) {
-  float2 y, dy;
-  act_and_grad2(act, x, y, dy, true);
-  return dy;
+// 16 float2 = one 32-column chunk of a row. MODE 0: v = act(v); 1: a = v, v = act(v); 2: a = act'(v), v = act(v);
+// 3: v = act'(v) (v holds pre-activations).
+template <int ACT, int MODE>
+__device__ __forceinline__ void act_chunk_t(float2 (&v)[16], float2 (&a)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float2 y, dy;
+    if constexpr (MODE == 2 || MODE == 3) act_and_grad2<ACT, true>(v[j], y, dy);
+    else act_and_grad2<ACT, false>(v[j], y, dy);
+    if constexpr (MODE == 1) a[j] = v[j];
+    if constexpr (MODE == 2) a[j] = dy;
+    v[j] = MODE == 3 ? dy : y;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void act_chunk(int act, float2 (&v)[16], float2 (&a)[16]) {
+  if (act == AVT_ACT_GELU_ERF) act_chunk_t<AVT_ACT_GELU_ERF, MODE>(v, a);
+  else if (act == AVT_ACT_GELU_TANH) act_chunk_t<AVT_ACT_GELU_TANH, MODE>(v, a);
+  else act_chunk_t<AVT_ACT_NONE, MODE>(v, a);
 }
 
 // ----------------------------------------------------------------------------- Philox4x32-10

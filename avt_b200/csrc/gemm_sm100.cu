@@ -324,17 +324,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (ep.aux_z) {
           float2 a[16];
-          if (ep.aux_mode == 1) {  // save act'(pre-activation): backward then only multiplies
-#pragma unroll
-            for (int j = 0; j < 16; ++j) act_and_grad2(ep.act, v[j], v[j], a[j], true);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              a[j] = v[j];
-              float2 unused;
-              act_and_grad2(ep.act, v[j], v[j], unused, false);
-            }
-          }
+          if (ep.aux_mode == 1) act_chunk<2>(ep.act, v, a);  // save act'(pre-activation): backward only multiplies
+          else act_chunk<1>(ep.act, v, a);
           if (p.tma_out) {
             tma_store_chunk(&tmAux, a, col0, row0);
           } else if (row_ok) {
@@ -343,22 +334,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 4 * j);
           }
         } else if (ep.act != AVT_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float2 unused;
-            act_and_grad2(ep.act, v[j], v[j], unused, false);
-          }
+          float2 unused[16];
+          act_chunk<0>(ep.act, v, unused);
         }
         if (ep.dact_z && (row_ok || p.tma_in)) {
+          float2 z[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t zz[4] = {zraw[j].x, zraw[j].y, zraw[j].z, zraw[j].w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 z2 = make_float2(bf16_lo(zz[q]), bf16_hi(zz[q]));
-              v[4 * j + q] = __fmul2_rn(v[4 * j + q], ep.dact_mode == 1 ? z2 : act_grad2(ep.dact, z2));
-            }
+            for (int q = 0; q < 4; ++q) z[4 * j + q] = make_float2(bf16_lo(zz[q]), bf16_hi(zz[q]));
           }
+          if (ep.dact_mode != 1) {
+            float2 unused[16];
+            act_chunk<3>(ep.dact, z, unused);   // z <- dact'(z)
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __fmul2_rn(v[j], z[j]);
         }
         if (ep.drop_p > 0.f) {
           const uint64_t g0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)col0) >> 2;
