@@ -46,6 +46,7 @@ _i64, _i32, _f32, _u64, _vp = C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_voi
 # name -> argtypes; every function returns int (0 = ok) unless listed in _SPECIAL.
 SIGNATURES = {
     "avt_check_device": [],
+    "avt_set_sm_limit": [_i32],
     "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp],
     "avt_layernorm_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
     "avt_layernorm_bwd": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp,

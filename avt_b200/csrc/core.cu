@@ -10,7 +10,15 @@ void set_last_error(const char* what, const char* detail, const char* file, int 
   snprintf(g_err, sizeof g_err, "%s: %s (%s:%d)", what, detail, file, line);
 }
 
+static int g_sm_limit = 0;
+
+int num_sms_physical();
 int num_sms() {
+  const int n = num_sms_physical();
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+
+int num_sms_physical() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -24,6 +32,10 @@ int num_sms() {
 }  // namespace avt
 
 extern "C" int avt_abi_version(void) { return 1; }
+extern "C" int avt_set_sm_limit(int n) {
+  avt::g_sm_limit = n > 0 ? (n & ~1) : 0;  // even, so CTA pairs still tile the budget
+  return AVT_OK;
+}
 extern "C" const char* avt_last_error(void) { return avt::g_err; }
 extern "C" int avt_check_device(void) {
   int dev = 0, major = 0;

@@ -25,10 +25,11 @@ class ParamPack:
 
     def __init__(self, named_params, device):
         named_params = list(named_params)
-        # small tensors (biases, LayerNorm, cls/pos) first: their gradients are produced by atomics and need
-        # zero-initialisation each backward; the big matrices are overwritten by the wgrad GEMMs.
-        small = [(n, p) for n, p in named_params if p.dim() < 2 or p.numel() < 1 << 14]
-        big = [(n, p) for n, p in named_params if not (p.dim() < 2 or p.numel() < 1 << 14)]
+        # vectors (biases, LayerNorm) first: their gradients are produced by atomics and need zero-initialisation
+        # each backward; matrices follow in module order (one layer's matrices are contiguous, so a layer's weight
+        # gradients can be all-reduced as one slice while the backward of earlier layers is still running).
+        small = [(n, p) for n, p in named_params if p.dim() < 2]
+        big = [(n, p) for n, p in named_params if p.dim() >= 2]
         self.names, self.slices, self.shapes = [], {}, {}
         off = 0
         for n, p in small + big:
@@ -144,6 +145,14 @@ class BlockStack:
     def __init__(self, spec: StackSpec, pack: ParamPack):
         self.s, self.pack = spec, pack
         self.ws = {}
+        self.layer_done_hook = None   # called with the layer index once that layer's parameter gradients are final
+
+    def layer_grad_range(self, i):
+        """[start, end) element range of layer i's weight matrices in the flat buffers (they are packed contiguously)."""
+        names = [v.format(i=i) + ".weight" for k, v in self.s.names.items() if k in ("qkv", "proj", "fc1", "fc2")]
+        lo = min(self.pack.slices[n][0] for n in names)
+        hi = max(self.pack.slices[n][0] + self.pack.slices[n][1] for n in names)
+        return lo, hi
 
     # ------------------------------------------------------------------ linear helpers (both weight layouts)
     def _fwd(self, x, wname, out, **ep):
@@ -294,4 +303,6 @@ class BlockStack:
             self._dgrad(w["dqkv"], nm["qkv"] + ".weight", w["dln"])
             ops.layernorm_bwd(w["dln"], xin, st[0], st[1], pk.wv(nm["ln1"] + ".weight"), dx,
                               pk.gv(nm["ln1"] + ".weight"), pk.gv(nm["ln1"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb)
+            if self.layer_done_hook is not None:
+                self.layer_done_hook(i)
         return dx, dxb

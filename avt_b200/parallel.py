@@ -8,6 +8,12 @@ launched from a hook inside the head's backward and overlaps the whole backbone 
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
+
+def _sm_count():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
 
 def allreduce_mean_(tensors, group=None, async_op=False):
     """In-place mean over ranks of each tensor; returns work handles when async_op."""
@@ -32,12 +38,15 @@ def allreduce_mean_(tensors, group=None, async_op=False):
 class FlatDataParallel:
     """Wraps an avt_b200.model.AVTModel-like module whose backbone.model / future_predictor own flat buffers."""
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, comm_sms=16):
         self.model, self.group = model, group
+        # SMs left to NCCL while gradient all-reduces overlap the backbone backward (persistent GEMM grids shrink)
+        self.comm_sms = comm_sms if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else 0
         self.vit, self.head = model.backbone.model, model.future_predictor
         self.vit.direct_grads = True
         self.head.direct_grads = True
         self._handles = []
+        self._layer_ranges = []
         self.head._grads_ready_hook = self._head_ready
         self.vit._grads_ready_hook = self._vit_ready
         self.other = [p for n, p in model.named_parameters()
@@ -50,10 +59,32 @@ class FlatDataParallel:
                 dist.broadcast(t, 0, group=self.group)
 
     def _head_ready(self):
+        if self.comm_sms:
+            _lib.lib().avt_set_sm_limit(_sm_count() - self.comm_sms)
         self._handles += allreduce_mean_([self.head.flat_buffers()[1]], self.group, async_op=True)
 
+    def _vit_layer_done(self, i):
+        """Layer i's weight gradients are final: reduce that slice now, overlapped with the rest of the backward."""
+        lo, hi = self.vit._stack.layer_grad_range(i)
+        self._layer_ranges.append((lo, hi))
+        self._handles += allreduce_mean_([self.vit.flat_buffers()[1][lo:hi]], self.group, async_op=True)
+
     def _vit_ready(self):
-        self._handles += allreduce_mean_([self.vit.flat_buffers()[1]], self.group, async_op=True)
+        g = self.vit.flat_buffers()[1]
+        if self.vit._stack.layer_done_hook is None:      # first backward: per-layer overlap is armed from the next step on
+            self.vit._stack.layer_done_hook = self._vit_layer_done
+            self._handles += allreduce_mean_([g], self.group, async_op=True)
+            return
+        # everything not covered by the per-layer slices (biases, LayerNorm, cls/pos, patch embedding, final norm)
+        rest, pos = [], 0
+        for lo, hi in sorted(self._layer_ranges):
+            if lo > pos:
+                rest.append(g[pos:lo])
+            pos = hi
+        if pos < g.numel():
+            rest.append(g[pos:])
+        self._layer_ranges = []
+        self._handles += allreduce_mean_(rest, self.group, async_op=True)
 
     def finish_backward(self):
         """Call after loss.backward(): reduces the remaining (torch-owned) gradients and waits for all handles."""
@@ -62,6 +93,8 @@ class FlatDataParallel:
         for h in self._handles:
             h.wait()
         self._handles = []
+        if self.comm_sms:
+            _lib.lib().avt_set_sm_limit(0)
 
     def flat_parameter_groups(self):
         """Three 'parameters' for a stock torch.optim optimizer: the two flat buffers (as leaf tensors whose .grad is

@@ -136,6 +136,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))   # the all-reduce shares the GPU with the backward
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().avt_check_device(), "avt_check_device")
 
@@ -144,7 +145,7 @@ def run_ours(args):
     dim = 1024 if "large" in args.model else 768
     model = AVTModel(args.model, dim, NUM_CLASSES).to(dev)
     model.train()
-    dp = FlatDataParallel(model)
+    dp = FlatDataParallel(model, comm_sms=args.comm_sms)
     video_h, target_h, sub_h = synth_batch(torch, B, T, rank, dev, pin=True)
     video_d, target_d, sub_d = video_h.to(dev), target_h.to(dev), sub_h.to(dev)
 
@@ -273,6 +274,7 @@ def main():
     ap.add_argument("--frames", type=int, default=10)
     ap.add_argument("--model", default="vit_base_patch16_224")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--comm-sms", type=int, default=16, help="SMs left to NCCL during the overlapped gradient all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

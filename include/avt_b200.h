@@ -34,6 +34,9 @@ int avt_abi_version(void);
 const char* avt_last_error(void);
 /* 0 if a compute-capability-10.x device is current, AVT_ERR_NO_GPU otherwise. */
 int avt_check_device(void);
+/* Cap the number of SMs the persistent kernels (GEMM) occupy; 0 = all. Used while an NCCL all-reduce runs
+ * concurrently: a persistent grid that assumes every SM is free is stretched 2x by the SMs the collective holds. */
+int avt_set_sm_limit(int n);
 
 /* Fused-epilogue description for avt_gemm_bf16. All pointers may be NULL (feature off).
  * Per output element (r, c), in this order:
