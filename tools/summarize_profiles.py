@@ -1,0 +1,56 @@
+"""Turn gpurun_out/ ncu artefacts into small text summaries under profiles/ (tracked).
+
+  python tools/summarize_profiles.py launches gpurun_out/launches5.csv profiles/r01_step_launches.md
+  python tools/summarize_profiles.py ncu gpurun_out/prof_gemm3.ncu-rep profiles/r01_gemm_fc1_ncu.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic"]
+
+
+def launches(src, dst):
+    with open(src) as f:
+        rows = list(csv.DictReader(l for l in f if not l.startswith("==")))
+    half = rows[len(rows) // 2:]          # tools/profile_step.py runs 2 steps: keep the second (steady state)
+    agg = collections.OrderedDict()
+    for r in half:
+        k = r["Kernel Name"].split("(")[0].replace("void ", "")
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r["Metric Value"])
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, "w") as o:
+        o.write(f"# ncu launch list, one training step (second of two), {len(half)} launches, sum {tot/1e6:.3f} ms\n")
+        o.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/profile_step.py 2\n")
+        o.write("# (per-launch times are cold-cache and serialised: compare SHARES)\n\n")
+        o.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            o.write(f"| `{k[:90]}` | {v[0]} | {v[1]/1e3:.1f} | {100*v[1]/tot:.1f}% |\n")
+    print("wrote", dst)
+
+
+def ncu(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    with open(dst, "w") as o:
+        o.write(f"# ncu --set full --clock-control none --import-source on  ({src})\n")
+        for d in data:
+            o.write(f"\n## {d[hdr.index('Kernel Name')][:110]}  grid {d[hdr.index('Grid Size')]} block {d[hdr.index('Block Size')]}\n")
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    o.write(f"{k:75s} {d[i]:>16s} {units[i]}\n")
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    {"launches": launches, "ncu": ncu}[sys.argv[1]](sys.argv[2], sys.argv[3])
