@@ -24,7 +24,7 @@ constexpr int kTcQBytes = 128 * 128;    // one Q tile: 128 rows x 64 bf16
 constexpr int kTcKVBytes = kTcKeys * 128;
 constexpr int kTcPBlk = 128 * 128;      // one P block: 128 rows x 64 keys bf16
 constexpr int kTcPBytes = 4 * kTcPBlk;  // keys padded to 256 in smem addressing (only 208 are read)
-constexpr int kTcSmem = 2 * kTcQBytes + 2 * kTcKVBytes + 2 * kTcPBytes + 1024 + 128;
+constexpr int kTcSmem = 2 * kTcQBytes + 2 * kTcKVBytes + 2 * kTcPBytes + 256;
 constexpr int kTcThreads = 288;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -36,38 +36,49 @@ __device__ __forceinline__ float fast_exp2(float x) {
 struct AttnTcParams {
   bf16* out;
   float* lse;
-  int N, H, D;
+  int N, H, D, F;
   float scale;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Persistent: each CTA walks (frame, head) items blockIdx.x, +gridDim.x, ... Single-buffered smem, but every
+  // buffer is refilled as soon as its last reader retires (Q/K after both S MMAs, V after both PV MMAs), so the
+  // next item's loads hide under the current item's softmax.
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                         // [2][128 x 64]   K-major SW128
   uint8_t* sK = sQ + 2 * kTcQBytes;           // [208 x 64]      K-major SW128 (B of S = Q K^T)
   uint8_t* sV = sK + kTcKVBytes;              // [208 x 64]      MN-major SW128 (B of O = P V)
   uint8_t* sP = sV + kTcKVBytes;              // [2][4][128 x 64] K-major SW128 (A of O = P V)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTcPBytes);
-  uint64_t* bar_load = bars;       // TMA -> MMA
-  uint64_t* bar_s = bars + 1;      // [2] S ready
-  uint64_t* bar_p = bars + 3;      // [2] P written (128 arrivals)
-  uint64_t* bar_o = bars + 5;      // [2] O ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_qk = bars;          // TMA (Q tiles + K) landed
+  uint64_t* bar_v = bars + 1;       // TMA (V) landed
+  uint64_t* bar_s = bars + 2;       // [2] S ready                      (MMA -> softmax warps)
+  uint64_t* bar_p = bars + 4;       // [2] P written, 128 arrivals      (softmax warps -> MMA)
+  uint64_t* bar_o = bars + 6;       // [2] O ready                      (MMA -> softmax warps)
+  uint64_t* bar_oread = bars + 8;   // [2] O drained from TMEM, 128 arrivals (S columns reusable)
+  uint64_t* bar_qkfree = bars + 10; // both S MMAs retired: sQ / sK reusable
+  uint64_t* bar_vfree = bars + 11;  // both PV MMAs retired: sV reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int N = p.N;
+  const int items = p.F * p.H;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
-      mbar_init(bar_load, 1);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_qkfree, 1);
+      mbar_init(bar_vfree, 1);
       for (int t = 0; t < 2; ++t) {
         mbar_init(&bar_s[t], 1);
         mbar_init(&bar_p[t], 128);
         mbar_init(&bar_o[t], 1);
+        mbar_init(&bar_oread[t], 128);
       }
       fence_mbar_init();
     }
@@ -81,46 +92,68 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    // ------------------------------------------------------------- control warp: TMA + MMA issue
+    // ------------------------------------------------------------- control warp: one lane issues TMA + MMA
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_load, 2 * kTcQBytes + 2 * kTcKVBytes);
-      tma_load_2d(&tmQ, bar_load, sQ, h * kTcHd, f * N);
-      tma_load_2d(&tmQ, bar_load, sQ + kTcQBytes, h * kTcHd, f * N + 128);
-      tma_load_2d(&tmKV, bar_load, sK, p.D + h * kTcHd, f * N);
-      tma_load_2d(&tmKV, bar_load, sV, 2 * p.D + h * kTcHd, f * N);
-    }
-    mbar_wait(bar_load, 0);
-    tc_fence_after_sync();
-    if (lane == 0) {
+      auto issue_qk = [&](int item) {
+        const int f = item / p.H, h = item % p.H;
+        mbar_arrive_expect_tx(bar_qk, 2 * kTcQBytes + kTcKVBytes);
+        tma_load_2d(&tmQ, bar_qk, sQ, h * kTcHd, f * N);
+        tma_load_2d(&tmQ, bar_qk, sQ + kTcQBytes, h * kTcHd, f * N + 128);
+        tma_load_2d(&tmKV, bar_qk, sK, p.D + h * kTcHd, f * N);
+      };
+      auto issue_v = [&](int item) {
+        const int f = item / p.H, h = item % p.H;
+        mbar_arrive_expect_tx(bar_v, kTcKVBytes);
+        tma_load_2d(&tmKV, bar_v, sV, 2 * p.D + h * kTcHd, f * N);
+      };
       constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, kTcKeys);
-      constexpr uint64_t desc_k = smem_desc_sw128(16, 1024);
-      const uint32_t aK = smem_u32(sK);
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t aQ = smem_u32(sQ + t * kTcQBytes);
+      constexpr uint32_t idesc_o = umma_idesc(1, 0, 1, 128, kTcHd);
+      constexpr uint64_t desc_k = smem_desc_sw128(16, 1024);     // K-major
+      constexpr uint64_t desc_v = smem_desc_sw128(8192, 1024);   // MN-major, one 64-wide block
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      if ((int)blockIdx.x < items) {
+        issue_qk(blockIdx.x);
+        issue_v(blockIdx.x);
+      }
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+        const uint32_t par = n & 1;
+        const int next = item + gridDim.x;
+        mbar_wait(bar_qk, par);
+        for (int t = 0; t < 2; ++t) {
+          if (n > 0) mbar_wait(&bar_oread[t], par ^ 1);   // previous item's O (aliases these S columns) was drained
+          tc_fence_after_sync();
+          const uint32_t aQ = smem_u32(sQ + t * kTcQBytes);
 #pragma unroll
-        for (int k = 0; k < kTcHd / 16; ++k)
-          umma_f16(tmem_base + 256 * t, smem_desc_addr(desc_k, aQ + k * 32), smem_desc_addr(desc_k, aK + k * 32), idesc_s,
-                   k > 0 ? 1u : 0u);
-        umma_commit(&bar_s[t]);
+          for (int k = 0; k < kTcHd / 16; ++k)
+            umma_f16(tmem_base + 256 * t, smem_desc_addr(desc_k, aQ + k * 32), smem_desc_addr(desc_k, aK + k * 32), idesc_s,
+                     k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[t]);
+        }
+        umma_commit(bar_qkfree);
+        if (next < items) {
+          mbar_wait(bar_qkfree, par);
+          issue_qk(next);
+        }
+        mbar_wait(bar_v, par);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&bar_p[t], par);
+          tc_fence_after_sync();
+          const uint32_t aP = smem_u32(sP + t * kTcPBytes);
+#pragma unroll
+          for (int k = 0; k < kTcKeys / 16; ++k)
+            umma_f16(tmem_base + 256 * t, smem_desc_addr(desc_k, aP + (k >> 2) * kTcPBlk + (k & 3) * 32),
+                     smem_desc_addr(desc_v, aV + k * 2048), idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(&bar_o[t]);
+        }
+        umma_commit(bar_vfree);
+        if (next < items) {
+          mbar_wait(bar_vfree, par);
+          issue_v(next);
+        }
       }
     }
     __syncwarp();
-    for (int t = 0; t < 2; ++t) {
-      mbar_wait(&bar_p[t], 0);
-      tc_fence_after_sync();
-      if (lane == 0) {
-        constexpr uint32_t idesc_o = umma_idesc(1, 0, 1, 128, kTcHd);
-        constexpr uint64_t desc_p = smem_desc_sw128(16, 1024);
-        constexpr uint64_t desc_v = smem_desc_sw128(8192, 1024);
-        const uint32_t aP = smem_u32(sP + t * kTcPBytes), aV = smem_u32(sV);
-#pragma unroll
-        for (int k = 0; k < kTcKeys / 16; ++k)
-          umma_f16(tmem_base + 256 * t, smem_desc_addr(desc_p, aP + (k >> 2) * kTcPBlk + (k & 3) * 32),
-                   smem_desc_addr(desc_v, aV + k * 2048), idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(&bar_o[t]);
-      }
-      __syncwarp();
-    }
   } else {
     // ------------------------------------------------------------- softmax + epilogue warpgroups
     const int t = warp >> 2;                    // query tile
@@ -128,101 +161,142 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int qrow = t * 128 + r;
     const uint32_t t_row = tmem_base + (uint32_t((warp & 3) * 32) << 16) + 256 * t;
     const float sl2 = p.scale * 1.4426950408889634f;
-    mbar_wait(&bar_s[t], 0);
-    tc_fence_after_sync();
-    // pass 1: row max over the valid keys
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 192; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j < N) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(t_row + 192, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (192 + j < N) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    // pass 2: e = exp(scale * (s - max)), row sum, P -> smem (bf16, swizzled K-major)
-    float sum = 0.f;
     uint8_t* prow = sP + t * kTcPBytes + r * 128;
     const int sw = r & 7;
-    const float mxs = mx * sl2;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 192; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + c0, v);
-      tmem_ld_wait();
-      float e[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        e[j] = (c0 + j < N) ? fast_exp2(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
-        sum += e[j];
-      }
-      uint8_t* blk = prow + (c0 >> 6) * kTcPBlk;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = ((c0 & 63) >> 3) + q;
-        *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) =
-            make_uint4(pack_bf16x2(e[8 * q], e[8 * q + 1]), pack_bf16x2(e[8 * q + 2], e[8 * q + 3]),
-                       pack_bf16x2(e[8 * q + 4], e[8 * q + 5]), pack_bf16x2(e[8 * q + 6], e[8 * q + 7]));
-      }
-    }
-    {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(t_row + 192, v);
-      tmem_ld_wait();
-      float e[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        e[j] = (192 + j < N) ? fast_exp2(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
-        sum += e[j];
-      }
-      uint8_t* blk = prow + 3 * kTcPBlk;
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(blk + ((q ^ sw) << 4)) =
-            make_uint4(pack_bf16x2(e[8 * q], e[8 * q + 1]), pack_bf16x2(e[8 * q + 2], e[8 * q + 3]),
-                       pack_bf16x2(e[8 * q + 4], e[8 * q + 5]), pack_bf16x2(e[8 * q + 6], e[8 * q + 7]));
-    }
-    fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before_sync();     // our tcgen05.ld of S are ordered before the MMA that overwrites those columns
-    mbar_arrive(&bar_p[t]);
-    // epilogue: O / sum -> bf16 -> global
-    mbar_wait(&bar_o[t], 0);
-    tc_fence_after_sync();
-    const float inv = 1.0f / sum;
     const bool ok = qrow < N;
-    bf16* orow = p.out + ((size_t)f * N + qrow) * p.D + h * kTcHd;
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+      const uint32_t par = n & 1;
+      const int f = item / p.H, h = item % p.H;
+      mbar_wait(&bar_s[t], par);
+      tc_fence_after_sync();
+      // pass 1: row max over the valid keys. Columns < nfull need no mask (N = 197: 6 of the 7 chunks); TMEM loads
+      // are double-buffered so the next chunk is in flight while the current one is reduced.
+      const int nfull = N >= 192 ? 192 : (N & ~31);
+      float mx = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(t_row, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 192; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(t_row + c0 + 32, vb);
+          if (c0 < nfull) {
 #pragma unroll
-    for (int c0 = 0; c0 < kTcHd; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + c0, v);
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < N) mx = fmaxf(mx, __uint_as_float(va[j]));
+          }
+          tmem_ld_wait();
+          if (c0 + 64 < 192) tmem_ld_32x32b_x32(t_row + c0 + 64, va);
+          if (c0 + 32 < nfull) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + 32 + j < N) mx = fmaxf(mx, __uint_as_float(vb[j]));
+          }
+        }
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + 192, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (192 + j < N) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      // pass 2: e = exp(scale * (s - max)), row sum, P -> smem (bf16, swizzled K-major)
+      float sum = 0.f;
+      const float mxs = mx * sl2;
+      auto emit = [&](const uint32_t (&v)[32], int c0) {
+        float e[32];
+        if (c0 < nfull) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -mxs));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = (c0 + j < N) ? fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -mxs)) : 0.f;
+        }
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s4[j & 3] += e[j];
+        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        uint8_t* blk = prow + (c0 >> 6) * kTcPBlk;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c0 & 63) >> 3) + q;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(e[8 * q], e[8 * q + 1]), pack_bf16x2(e[8 * q + 2], e[8 * q + 3]),
+                         pack_bf16x2(e[8 * q + 4], e[8 * q + 5]), pack_bf16x2(e[8 * q + 6], e[8 * q + 7]));
+        }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(t_row, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 192; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(t_row + c0 + 32, vb);
+          emit(va, c0);
+          tmem_ld_wait();
+          if (c0 + 64 < 192) tmem_ld_32x32b_x32(t_row + c0 + 64, va);
+          emit(vb, c0 + 32);
+        }
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + 192, v);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          e[j] = (192 + j < N) ? fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -mxs)) : 0.f;
+          sum += e[j];
+        }
+        uint8_t* blk = prow + 3 * kTcPBlk;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          *reinterpret_cast<uint4*>(blk + ((q ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(e[8 * q], e[8 * q + 1]), pack_bf16x2(e[8 * q + 2], e[8 * q + 3]),
+                         pack_bf16x2(e[8 * q + 4], e[8 * q + 5]), pack_bf16x2(e[8 * q + 6], e[8 * q + 7]));
+      }
+      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before_sync();     // our tcgen05.ld of S are ordered before the MMA that overwrites those columns
+      mbar_arrive(&bar_p[t]);
+      // epilogue: O / sum -> bf16 -> global
+      mbar_wait(&bar_o[t], par);
+      tc_fence_after_sync();
+      const float inv = 1.0f / sum;
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(t_row, o0);
+      tmem_ld_32x32b_x32(t_row + 32, o1);
       tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bar_oread[t]);   // the next item's S MMA may overwrite these columns now
       if (ok) {
+        bf16* orow = p.out + ((size_t)f * N + qrow) * p.D + h * kTcHd;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(orow + c0 + 8 * q) = make_uint4(
-              pack_bf16x2(__uint_as_float(v[8 * q]) * inv, __uint_as_float(v[8 * q + 1]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv));
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<uint4*>(orow + 8 * q) = make_uint4(
+              pack_bf16x2(__uint_as_float(o0[8 * q]) * inv, __uint_as_float(o0[8 * q + 1]) * inv),
+              pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv),
+              pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv),
+              pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv));
+          *reinterpret_cast<uint4*>(orow + 32 + 8 * q) = make_uint4(
+              pack_bf16x2(__uint_as_float(o1[8 * q]) * inv, __uint_as_float(o1[8 * q + 1]) * inv),
+              pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv),
+              pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv),
+              pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv));
+        }
+        if (p.lse) p.lse[((size_t)f * p.H + h) * N + qrow] = mx * p.scale + __logf(sum);
       }
     }
-    if (ok && p.lse) p.lse[((size_t)f * p.H + h) * N + qrow] = mx * p.scale + __logf(sum);
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
-
 
 // ------------------------------------------------------------------------------------------------ backward
 // One CTA per (frame, head), "keys on lanes": for key tile j (128 keys) and query half qh (128 / 80 queries)
@@ -235,6 +309,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int kBwTile = kTcKeys * 128;            // 208 rows x 64 bf16
 constexpr int kBwBlk = 128 * 128;                 // [128 x 64] bf16 block
 constexpr int kBwSmem = 4 * kBwTile + 4 * kBwBlk + 2 * kTcKeys * 4 + 1024 + 128;
+
+#ifdef AVT_ATTN_TRACE
+#define TRACE_DECL __shared__ unsigned long long trace_t[64]; __shared__ int trace_id[64]; __shared__ int trace_n;
+#define TRACE_INIT if (threadIdx.x == 0) trace_n = 0;
+#define TRACE(id) do { if (blockIdx.x == 0) { int i_ = atomicAdd(&trace_n, 1); if (i_ < 64) { trace_t[i_] = global_timer_ns(); trace_id[i_] = (id); } } } while (0)
+#define TRACE_DUMP if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < trace_n && i_ < 64; ++i_) printf("trace %d %llu\n", trace_id[i_], trace_t[i_] - trace_t[0]); }
+#else
+#define TRACE_DECL
+#define TRACE_INIT
+#define TRACE(id)
+#define TRACE_DUMP
+#endif
 
 struct AttnTcBwdParams {
   const bf16* out;    // forward output  [F*N, D]
@@ -269,9 +355,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int N = p.N;
+  TRACE_DECL
+  TRACE_INIT
 
   if (warp == 8) {
     if (lane == 0) {
+      TRACE(0);
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
       mbar_init(bar_load, 1);
@@ -280,6 +369,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_init(bar_d, 1);
       mbar_init(bar_out, 256);
       fence_mbar_init();
+      // the loads do not depend on TMEM: get them in flight before the allocation and the block-wide sync
+      mbar_arrive_expect_tx(bar_load, 4 * kBwTile);
+      tma_load_2d(&tmQKV, bar_load, sQ, h * kTcHd, f * N);
+      tma_load_2d(&tmQKV, bar_load, sK, p.D + h * kTcHd, f * N);
+      tma_load_2d(&tmQKV, bar_load, sV, 2 * p.D + h * kTcHd, f * N);
+      tma_load_2d(&tmDO, bar_load, sG, h * kTcHd, f * N);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
@@ -292,40 +387,40 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   if (warp == 8) {
     // ------------------------------------------------------------- control warp
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_load, 4 * kBwTile);
-      tma_load_2d(&tmQKV, bar_load, sQ, h * kTcHd, f * N);
-      tma_load_2d(&tmQKV, bar_load, sK, p.D + h * kTcHd, f * N);
-      tma_load_2d(&tmQKV, bar_load, sV, 2 * p.D + h * kTcHd, f * N);
-      tma_load_2d(&tmDO, bar_load, sG, h * kTcHd, f * N);
-    }
     mbar_wait(bar_load, 0);
+    if (lane == 0) TRACE(1);
     tc_fence_after_sync();
     constexpr uint64_t dK_major = smem_desc_sw128(16, 1024);      // K-major operand
     constexpr uint64_t dMN_1blk = smem_desc_sw128(8192, 1024);    // MN-major, one 64-wide block (N = 64)
     constexpr uint64_t dMN_2blk = smem_desc_sw128(kBwBlk, 1024);  // MN-major, two 64-wide blocks 16 KB apart (M = 128)
     const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aG = smem_u32(sG), aP = smem_u32(sP),
                    aS = smem_u32(sS);
+    // S^T / dP^T of iteration it+1 are issued right behind the dV/dK/dQ MMAs of iteration it (the tensor pipe runs
+    // them in order; the worker warps have already drained the S^T / dP^T columns when they signalled bar_p).
+    auto issue_mma1 = [&](int it) {
+      const int j = it >> 1, qh = it & 1;
+      const int ncols = qh == 0 ? 128 : kTcKeys - 128;
+      const uint32_t idesc1 = umma_idesc(1, 0, 0, 128, ncols);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tm + 0, smem_desc_addr(dK_major, aK + j * kBwBlk + k * 32), smem_desc_addr(dK_major, aQ + qh * kBwBlk + k * 32),
+                 idesc1, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tm + 128, smem_desc_addr(dK_major, aV + j * kBwBlk + k * 32), smem_desc_addr(dK_major, aG + qh * kBwBlk + k * 32),
+                 idesc1, k > 0);
+      umma_commit(bar_s);
+    };
+    if (lane == 0) issue_mma1(0);
+    __syncwarp();
     for (int it = 0; it < 4; ++it) {
       const int j = it >> 1, qh = it & 1;
       const int ncols = qh == 0 ? 128 : kTcKeys - 128;
-      if (lane == 0) {
-        const uint32_t idesc1 = umma_idesc(1, 0, 0, 128, ncols);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tm + 0, smem_desc_addr(dK_major, aK + j * kBwBlk + k * 32), smem_desc_addr(dK_major, aQ + qh * kBwBlk + k * 32),
-                   idesc1, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tm + 128, smem_desc_addr(dK_major, aV + j * kBwBlk + k * 32), smem_desc_addr(dK_major, aG + qh * kBwBlk + k * 32),
-                   idesc1, k > 0);
-        umma_commit(bar_s);
-      }
-      __syncwarp();
       mbar_wait(bar_p, it & 1);
       if (it == 2) mbar_wait(bar_out, 0);   // dV_0 / dK_0 have been read out of TMEM
       tc_fence_after_sync();
       if (lane == 0) {
+        TRACE(100 + it);
         constexpr uint32_t idesc_kv = umma_idesc(1, 0, 1, 128, kTcHd);
         constexpr uint32_t idesc_q = umma_idesc(1, 1, 1, 128, kTcHd);
         const int ks = ncols / 16;
@@ -341,6 +436,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           umma_f16(tm + 384 + 64 * qh, smem_desc_addr(dMN_2blk, aS + k * 2048), smem_desc_addr(dMN_1blk, aK + j * kBwBlk + k * 2048),
                    idesc_q, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_d);
+        if (it < 3) issue_mma1(it + 1);
+        TRACE(110 + it);
       }
       __syncwarp();
     }
@@ -370,6 +467,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         sLse[q] = l;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) TRACE(2);
     }
     bf16* dbase = p.dqkv + (size_t)f * N * 3 * p.D + h * kTcHd;
     for (int it = 0; it < 4; ++it) {
@@ -378,22 +476,34 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const bool key_ok = key < N;
       const int nchunk = (qh == 0 || ch == 0) ? 4 : 1;     // 16-column chunks handled by this warp
       mbar_wait(bar_s, it & 1);
+      if (threadIdx.x == 0) TRACE(200 + it);
       if (it > 0) mbar_wait(bar_d, (it - 1) & 1);          // previous MMAs have finished reading sP / sS
+      if (threadIdx.x == 0) TRACE(210 + it);
       tc_fence_after_sync();
       for (int c = 0; c < nchunk; ++c) {
         const int c0 = ch * 64 + c * 16;                   // column within this query half
+        const int q0 = qh * 128 + c0;
         uint32_t sv[16], dv[16];
         tmem_ld_32x32b_x16(t_lane + c0, sv);
         tmem_ld_32x32b_x16(t_lane + 128 + c0, dv);
+        float ls[16], dl[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 4) {   // broadcast smem reads, issued while the TMEM loads are in flight
+          const float4 a4 = *reinterpret_cast<const float4*>(sLse + q0 + jj);
+          const float4 b4 = *reinterpret_cast<const float4*>(sDelta + q0 + jj);
+          ls[jj] = a4.x; ls[jj + 1] = a4.y; ls[jj + 2] = a4.z; ls[jj + 3] = a4.w;
+          dl[jj] = b4.x; dl[jj + 1] = b4.y; dl[jj + 2] = b4.z; dl[jj + 3] = b4.w;
+        }
         tmem_ld_wait();
         float pv[16], ds[16];
+        const bool qmask = q0 + 16 > N;        // only the chunk that straddles N needs per-column masking
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const int q = qh * 128 + c0 + jj;
-          const bool ok = key_ok && q < N;
-          const float pr = ok ? fast_exp2(__uint_as_float(sv[jj]) * sl2 - sLse[q]) : 0.f;
+          float pr = fast_exp2(fmaf(__uint_as_float(sv[jj]), sl2, -ls[jj]));
+          if (qmask && q0 + jj >= N) pr = 0.f;
+          pr = key_ok ? pr : 0.f;
           pv[jj] = pr;
-          ds[jj] = pr * (__uint_as_float(dv[jj]) - sDelta[q]) * p.scale;
+          ds[jj] = pr * (__uint_as_float(dv[jj]) - dl[jj]) * p.scale;
         }
         const uint32_t off = (c0 >> 6) * kBwBlk + kr * 128;
         const int chunk = (c0 & 63) >> 3;
@@ -410,6 +520,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
+      if (threadIdx.x == 0) TRACE(220 + it);
       mbar_arrive(bar_p);
       if (qh == 1) {
         // dV_j / dK_j are complete once this iteration's MMAs retire: read them out (32 columns per warp)
@@ -438,6 +549,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         tc_fence_before_sync();
         if (it == 1) mbar_arrive(bar_out);
+        if (threadIdx.x == 0) TRACE(230 + it);
       }
     }
     // dQ: warp (quarter, ch) reads query tile `ch`, rows quarter*32 + lane, all 64 columns
@@ -462,8 +574,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
   }
 
+  if (threadIdx.x == 0) TRACE(999);
   tc_fence_before_sync();
   __syncthreads();
+  TRACE_DUMP
   if (warp == 8) tmem_dealloc(tm, 512);
 }
 
@@ -485,8 +599,9 @@ extern "C" int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int 
     configured = true;
   }
   AttnTcParams p;
-  p.out = reinterpret_cast<bf16*>(out); p.lse = lse; p.N = N; p.H = H; p.D = D; p.scale = scale;
-  attn_tc_fwd_kernel<<<F * H, kTcThreads, kTcSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+  p.out = reinterpret_cast<bf16*>(out); p.lse = lse; p.N = N; p.H = H; p.D = D; p.F = F; p.scale = scale;
+  const int grid = F * H < num_sms() ? F * H : num_sms();
+  attn_tc_fwd_kernel<<<grid, kTcThreads, kTcSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
