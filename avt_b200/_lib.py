@@ -47,7 +47,8 @@ _i64, _i32, _f32, _u64, _vp = C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_voi
 SIGNATURES = {
     "avt_check_device": [],
     "avt_set_sm_limit": [_i32],
-    "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp],
+    "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp, _i64,
+                      _vp],
     "avt_layernorm_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
     "avt_layernorm_bwd": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
                           _i32, _vp, _i64, _vp],
@@ -94,7 +95,7 @@ def check(rc, what=""):
 
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim)
-_KERNELS_PER_CALL = {"avt_layernorm_bwd": 2, "avt_frame_sum_grads": 2}
+_KERNELS_PER_CALL = {"avt_layernorm_bwd": 2, "avt_frame_sum_grads": 2}  # (+1 finishing kernel per two-pass split-K GEMM)
 launch_count = 0
 
 

@@ -114,6 +114,7 @@ class VisionTransformer(nn.Module):
                                 act=ops.ACT_GELU_ERF, conv1d=False, causal=False, names=_TIMM_NAMES,
                                 attn_impl=self.attn_impl)
         self._stack = engine.BlockStack(spec, self._pack)
+        self._stack.grads_prezeroed = True     # _run_backward zeroes the whole flat gradient buffer first
         self._aux = {}
         if self.direct_grads:
             self._pack.attach_grads()
@@ -177,7 +178,7 @@ class VisionTransformer(nn.Module):
         st.backward(w, dx, dxb)
         A = self._aux[("patch", M)]
         sk = engine._split_k_for(D, Kp, M, 256)
-        ops.gemm(dxb, A, pk.gv("patch_embed.proj.weight").view(D, Kp), a_mn=True, b_mn=True, split_k=sk)
+        ops.gemm(dxb, A, pk.gv("patch_embed.proj.weight").view(D, Kp), a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1)
         ops.frame_sum_grads(dx, F, ntok, D, self._aux[("fsum", ntok)], dpos=pk.gv("pos_embed"), dcls=pk.gv("cls_token"),
                             dbias=pk.gv("patch_embed.proj.bias"), accumulate=False)
         if self._grads_ready_hook is not None:

@@ -50,8 +50,9 @@ struct GemmCfg {
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks, split_k, kb_per_split;
-  int tma_out;  // bf16 `out` (and aux_z) leave through TMA stores
+  int tma_out;  // `out` (and bf16 aux_z) leave through TMA stores: 1 = bf16 out, 2 = fp32 out (plain overwrite)
   int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
+  int split_slices;  // split-K partials go to out + split*M*ldo (deterministic two-pass) instead of atomics
   avt_epilogue_t ep;
 };
 
@@ -236,6 +237,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       ++n_st;
     };
+    auto tma_store_chunk_f32 = [&](const CUtensorMap* tm, const float2* v, int col0, int row0) {
+      // 32 rows x 32 fp32 = 4 KB: both out slots as one buffer, 128-byte rows, SWIZZLE_128B (chunk ^= row & 7)
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(out_slots + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tm, out_slots, col0, row0);
+        tma_store_commit();
+      }
+    };
     auto issue_in = [&](int col0, int row0) {   // prefetch a 32 x 32 bf16 block of dact_z into a staging slot
       if (lane == 0) {
         uint64_t* bar = &in_bar[n_in_issued & 1];
@@ -248,6 +264,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     for (int unit = unit0; unit < num_units; unit += unit_stride) {
       const int tile = unit / p.split_k;
+      const int split = unit % p.split_k;
       const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
       const int row0 = m0 + quarter * 32;
@@ -326,7 +343,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float2 a[16];
           if (ep.aux_mode == 1) act_chunk<2>(ep.act, v, a);  // save act'(pre-activation): backward only multiplies
           else act_chunk<1>(ep.act, v, a);
-          if (p.tma_out) {
+          if (p.tma_out == 1) {
             tma_store_chunk(&tmAux, a, col0, row0);
           } else if (row_ok) {
             uint4* zp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col0);
@@ -372,12 +389,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[2 * j + 1] = __fadd2_rn(v[2 * j + 1], make_float2(b.z, b.w));
           }
         }
-        if (p.tma_out) {
+        if (p.tma_out == 1) {
           tma_store_chunk(&tmOut, v, col0, row0);
+        } else if (p.tma_out == 2) {
+          tma_store_chunk_f32(&tmOut, v, col0, row0);
         } else if (row_ok) {
           if (ep.out_fp32) {
             float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-            if (p.split_k > 1) {
+            if (p.split_slices) {
+              op += (size_t)split * p.M * ep.ldo;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+            } else if (p.split_k > 1) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 atomicAdd(reinterpret_cast<float4*>(op + 4 * j), make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y));
@@ -421,6 +445,73 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// Finishing pass of a split-K GEMM whose partial sums were accumulated (fp32 atomics) into `acc`: applies the same
+// epilogue as the fused path. Only used for the weight-streaming M <= 128 GEMMs of AVT-h (80 x N elements).
+__global__ void __launch_bounds__(256)
+epilogue_apply_kernel(const float* __restrict__ acc, int nslices, int M, int N, const avt_epilogue_t ep) {
+  const int64_t total4 = (int64_t)M * N / 4;
+  const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total4; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = g * 4;
+    const int row = (int)(e0 / N), col = (int)(e0 % N);
+    float4 a4 = *reinterpret_cast<const float4*>(acc + e0);
+    for (int sl = 1; sl < nslices; ++sl) {   // fixed summation order: bit-reproducible
+      const float4 b4 = *reinterpret_cast<const float4*>(acc + (size_t)sl * M * N + e0);
+      a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+    }
+    float v[4] = {a4.x * ep.alpha, a4.y * ep.alpha, a4.z * ep.alpha, a4.w * ep.alpha};
+    if (ep.bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (ep.pos_period > 0) {
+      const int t = row % ep.pos_period;
+      if (t == 0 && ep.cls) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col));
+        v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
+      }
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.pos + (size_t)t * N + col));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (ep.aux_z) {
+      float a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] = ep.aux_mode == 1 ? apply_act_grad(ep.act, v[j]) : v[j];
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col) =
+          make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(ep.act, v[j]);
+    if (ep.dact_z) {
+      const uint2 z = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col);
+      const float zz[4] = {bf16_lo(z.x), bf16_hi(z.x), bf16_lo(z.y), bf16_hi(z.y)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= ep.dact_mode == 1 ? zz[j] : apply_act_grad(ep.dact, zz[j]);
+    }
+    if (ep.drop_p > 0.f) {
+      const uint32_t keep = dropout_keep4(ep.drop_seed, ep.drop_offset, (uint64_t)g, ep.drop_p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+    }
+    if (ep.residual) {
+      const float4 b = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col);
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (ep.out_fp32) {
+      float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
+      float4 o = make_float4(v[0], v[1], v[2], v[3]);
+      if (ep.accumulate) {
+        const float4 c = *reinterpret_cast<const float4*>(op);
+        o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+      }
+      *reinterpret_cast<float4*>(op) = o;
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo + col) =
+          make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -439,19 +530,25 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; swizzle_bytes in {64, 128}.
+// 2-D tensor map: `inner` contiguous elements, `outer` rows of `ld` elements; swizzle_bytes in {64, 128}.
+static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                        uint32_t box_outer, int swizzle_bytes, bool fp32);
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                       uint32_t box_outer, int swizzle_bytes) {
+  return make_tmap_2d(tm, base, inner, outer, ld, box_inner, box_outer, swizzle_bytes, false);
+}
+static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                        uint32_t box_outer, int swizzle_bytes, bool fp32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled", "driver entry point not available", __FILE__, __LINE__);
     return AVT_ERR_CUDA;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (fp32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(tm, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -510,7 +607,7 @@ using namespace avt;
 
 extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M,
                              int64_t N, int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group,
-                             void* stream) {
+                             void* workspace, int64_t workspace_bytes, void* stream) {
   AVT_REQUIRE(A && B && ep && ep->out, "null pointer");
   AVT_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
   AVT_REQUIRE(N % 32 == 0, "N must be a multiple of 32");
@@ -523,10 +620,15 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   AVT_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 64, 128 or 256");
   if (cta_group == 2 && block_n == 64) cta_group = 1;
   if (split_k < 1) split_k = 1;
-  if (split_k > 1) {
-    AVT_REQUIRE(ep->out_fp32 && !ep->bias && !ep->aux_z && !ep->dact_z && !ep->residual && ep->act == AVT_ACT_NONE &&
-                    ep->drop_p == 0.f && ep->pos_period == 0,
-                "split_k > 1 supports only fp32 accumulation into out");
+  const bool plain_acc = ep->out_fp32 && !ep->bias && !ep->aux_z && !ep->dact_z && !ep->residual && ep->act == AVT_ACT_NONE &&
+                         ep->drop_p == 0.f && ep->pos_period == 0 && (ep->alpha == 0.f || ep->alpha == 1.f);
+  // partial sums into `workspace` slices + epilogue_apply_kernel whenever a workspace is supplied (deterministic);
+  // fp32 atomics straight into `out` only for the plain accumulation without workspace (weight gradients)
+  const bool two_pass = split_k > 1 && (!plain_acc || workspace != nullptr);
+  if (two_pass) {
+    AVT_REQUIRE(workspace && workspace_bytes >= (int64_t)split_k * M * N * 4,
+                "split_k with a fused epilogue needs a split_k*M*N fp32 workspace");
+    AVT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
   }
   if (ep->residual) AVT_REQUIRE(ep->ldr % 4 == 0, "residual ld must be a multiple of 4");
   if (ep->aux_z || ep->dact_z) AVT_REQUIRE(ep->ldz % 8 == 0, "z ld must be a multiple of 8");
@@ -541,8 +643,23 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.ep = *ep;
   if (p.ep.alpha == 0.f) p.ep.alpha = 1.0f;
-  p.tma_out = (!ep->out_fp32 && p.split_k == 1) ? 1 : 0;
-  p.tma_in = ep->dact_z ? 1 : 0;
+  avt_epilogue_t finish = p.ep;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!two_pass && p.split_k > 1 && !p.ep.accumulate) {
+    // plain fp32 output, overwrite semantics: the atomics need a zeroed destination
+    AVT_CUDA_OK(cudaMemset2DAsync(p.ep.out, (size_t)p.ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s));
+  }
+  p.split_slices = 0;
+  if (two_pass && p.split_k > 1) {
+    p.split_slices = 1;
+    p.ep = avt_epilogue_t{};
+    p.ep.alpha = 1.0f;
+    p.ep.out = workspace;
+    p.ep.ldo = N;
+    p.ep.out_fp32 = 1;
+  }
+  p.tma_out = p.split_k > 1 ? 0 : (!p.ep.out_fp32 ? 1 : (p.ep.accumulate ? 0 : 2));
+  p.tma_in = p.ep.dact_z ? 1 : 0;
 
   GemmMaps tm;
   int rc;
@@ -556,21 +673,31 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   tm.out = tm.a;
   tm.aux = tm.a;
   tm.in = tm.a;
-  if (p.tma_in && (rc = make_tmap_bf16_2d(&tm.in, ep->dact_z, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldz, 32, 32, 64))) return rc;
+  if (p.tma_in && (rc = make_tmap_bf16_2d(&tm.in, p.ep.dact_z, (uint64_t)N, (uint64_t)M, (uint64_t)p.ep.ldz, 32, 32, 64))) return rc;
   if (p.tma_out) {
-    if ((rc = make_tmap_bf16_2d(&tm.out, ep->out, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldo, 32, 32, 64))) return rc;
-    if (ep->aux_z && (rc = make_tmap_bf16_2d(&tm.aux, ep->aux_z, (uint64_t)N, (uint64_t)M, (uint64_t)ep->ldz, 32, 32, 64)))
+    if ((rc = make_tmap_2d(&tm.out, p.ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)p.ep.ldo, 32, 32, p.tma_out == 2 ? 128 : 64,
+                           p.tma_out == 2)))
+      return rc;
+    if (p.ep.aux_z && p.tma_out == 1 && (rc = make_tmap_bf16_2d(&tm.aux, p.ep.aux_z, (uint64_t)N, (uint64_t)M, (uint64_t)p.ep.ldz, 32, 32, 64)))
       return rc;
   }
 
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (cta_group == 2) {
-    if (block_n == 128) return dispatch_major<128, 2>(a_mn, b_mn, tm, p, s);
-    return dispatch_major<256, 2>(a_mn, b_mn, tm, p, s);
+    rc = block_n == 128 ? dispatch_major<128, 2>(a_mn, b_mn, tm, p, s) : dispatch_major<256, 2>(a_mn, b_mn, tm, p, s);
+  } else {
+    switch (block_n) {
+      case 64: rc = dispatch_major<64, 1>(a_mn, b_mn, tm, p, s); break;
+      case 128: rc = dispatch_major<128, 1>(a_mn, b_mn, tm, p, s); break;
+      default: rc = dispatch_major<256, 1>(a_mn, b_mn, tm, p, s); break;
+    }
   }
-  switch (block_n) {
-    case 64: return dispatch_major<64, 1>(a_mn, b_mn, tm, p, s);
-    case 128: return dispatch_major<128, 1>(a_mn, b_mn, tm, p, s);
-    default: return dispatch_major<256, 1>(a_mn, b_mn, tm, p, s);
+  if (rc) return rc;
+  if (two_pass && p.split_k > 1) {
+    const int64_t total4 = M * N / 4;
+    int blocks = (int)((total4 + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    epilogue_apply_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(workspace), p.split_k, (int)M, (int)N, finish);
+    AVT_CUDA_OK(cudaGetLastError());
   }
+  return AVT_OK;
 }

@@ -134,6 +134,17 @@ class StackSpec:
     attn_impl: str = "simt"  # "simt" | "tc" (tcgen05 kernel for N=197, hd=64)
 
 
+def small_m_split(M, N, K, sms=148):
+    """Split-K factor for the weight-streaming GEMMs (M <= 128 rows: one 128 x 64 tile per CTA would leave most SMs
+    idle while a few CTAs stream the whole weight matrix). 1 = no split."""
+    if M > 128:
+        return 1
+    tiles = (N + 63) // 64
+    kblocks = (K + 63) // 64
+    want = max(1, (sms + tiles - 1) // tiles)
+    return max(1, min(want, kblocks // 4))
+
+
 def _split_k_for(m_w, n_w, k_rows, block_n, sms=148):
     tiles = ((m_w + 127) // 128) * ((n_w + block_n - 1) // block_n)
     kblocks = (k_rows + 63) // 64
@@ -145,6 +156,7 @@ class BlockStack:
     def __init__(self, spec: StackSpec, pack: ParamPack):
         self.s, self.pack = spec, pack
         self.ws = {}
+        self.grads_prezeroed = False  # the owner zeroes pack.g before backward (split-K wgrads then just accumulate)
         self.layer_done_hook = None   # called with the layer index once that layer's parameter gradients are final
 
     def layer_grad_range(self, i):
@@ -156,20 +168,30 @@ class BlockStack:
 
     # ------------------------------------------------------------------ linear helpers (both weight layouts)
     def _fwd(self, x, wname, out, **ep):
-        ops.gemm(x, self.pack.bv(wname), out, b_mn=self.s.conv1d, **ep)
+        sk = small_m_split(out.shape[0], out.shape[1], x.shape[1])
+        ops.gemm(x, self.pack.bv(wname), out, b_mn=self.s.conv1d, split_k=sk, workspace=self._gemm_ws(out, sk), **ep)
 
     def _dgrad(self, dy, wname, out, **ep):
-        ops.gemm(dy, self.pack.bv(wname), out, b_mn=not self.s.conv1d, **ep)
+        sk = small_m_split(out.shape[0], out.shape[1], dy.shape[1])
+        ops.gemm(dy, self.pack.bv(wname), out, b_mn=not self.s.conv1d, split_k=sk, workspace=self._gemm_ws(out, sk), **ep)
+
+    def _gemm_ws(self, out, sk):
+        if sk <= 1:
+            return None
+        n = sk * out.shape[0] * out.shape[1]
+        if getattr(self, "_ws_buf", None) is None or self._ws_buf.numel() < n:
+            self._ws_buf = torch.empty(n, dtype=torch.float32, device=out.device)
+        return self._ws_buf
 
     def _wgrad(self, x, dy, wname, bname):
         dW = self.pack.gv(wname)
         rows = x.shape[0]
         if self.s.conv1d:   # dW[in, out] = X^T dY
             sk = _split_k_for(x.shape[1], dy.shape[1], rows, 256)
-            ops.gemm(x, dy, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=False)
+            ops.gemm(x, dy, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed)
         else:               # dW[out, in] = dY^T X
             sk = _split_k_for(dy.shape[1], x.shape[1], rows, 256)
-            ops.gemm(dy, x, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=False)
+            ops.gemm(dy, x, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed)
         if bname is not None:
             ops.colsum(dy, self.pack.gv(bname))
 

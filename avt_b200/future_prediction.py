@@ -184,14 +184,17 @@ class AVTh(nn.Module):
         p_embd = self.embd_pdrop if drop else 0.0
         ops.cast_bf16(feats2d.contiguous().float(), a["xb"])
         # h0 = dropout(encoder(feats) + wpe[0:T])   (reference :163 + HF GPT2Model.forward)
+        sk = engine.small_m_split(M, Dh, C)
         ops.gemm(a["xb"], pk.bv("encoder.weight"), w["x"][0], pos=pk.wv("gpt_model.wpe.weight")[:T], pos_period=T,
-                 drop_p=p_embd, drop_seed=seed, drop_offset=off + (255 << 28))
+                 drop_p=p_embd, drop_seed=seed, drop_offset=off + (255 << 28), split_k=sk,
+                 workspace=st._gemm_ws(w["x"][0], sk))
         xmid, y = st.forward(w, B, T, train_graph, rng=(seed, off), dropout=drop)
         xf = st._xbuf(w, train_graph, 2 * self.n_layer)
         ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, a["lnf"],
                           a["fst"][0], a["fst"][1], add=y, x_out=xf)
         decoded = torch.empty(M, C, dtype=torch.float32, device=dev)
-        ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded)
+        sk = engine.small_m_split(M, C, Dh)
+        ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded, split_k=sk, workspace=st._gemm_ws(decoded, sk))
         return decoded, (w, xf, B, T, p_embd, seed, off)
 
     def _run_backward(self, saved, ddec):
@@ -202,7 +205,9 @@ class AVTh(nn.Module):
         pk.zero_small_grads()
         ops.cast_bf16(ddec.contiguous().float(), a["db"])
         ops.gemm(a["db"], a["lnf"], pk.gv("decoder.weight"), a_mn=True, b_mn=True)          # dWdec = ddec^T lnf
-        ops.gemm(a["db"], pk.bv("decoder.weight"), a["dlnf"], b_mn=True)                     # dlnf = ddec Wdec
+        sk = engine.small_m_split(M, Dh, C)
+        ops.gemm(a["db"], pk.bv("decoder.weight"), a["dlnf"], b_mn=True, split_k=sk,        # dlnf = ddec Wdec
+                 workspace=st._gemm_ws(a["dlnf"], sk))
         dx, dxb = w["dx"], w["dxb"]
         ops.layernorm_bwd(a["dlnf"], xf, a["fst"][0], a["fst"][1], pk.wv("gpt_model.ln_f.weight"), dx,
                           pk.gv("gpt_model.ln_f.weight"), pk.gv("gpt_model.ln_f.bias"), w["lnws"], dx_bf16=dxb)
@@ -214,7 +219,9 @@ class AVTh(nn.Module):
         ops.frame_sum_grads(g32, B, T, Dh, a["fsum"], dpos=pk.gv("gpt_model.wpe.weight")[:T], accumulate=False)
         ops.gemm(gb, a["xb"], pk.gv("encoder.weight"), a_mn=True, b_mn=True)                 # dWenc = g^T feats
         dfeats = torch.empty(M, C, dtype=torch.float32, device=ddec.device)
-        ops.gemm(gb, pk.bv("encoder.weight"), dfeats, b_mn=True)                             # dfeats = g Wenc
+        sk = engine.small_m_split(M, C, Dh)
+        ops.gemm(gb, pk.bv("encoder.weight"), dfeats, b_mn=True, split_k=sk,                 # dfeats = g Wenc
+                 workspace=st._gemm_ws(dfeats, sk))
         if self._grads_ready_hook is not None:
             self._grads_ready_hook()
         return dfeats

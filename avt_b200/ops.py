@@ -26,7 +26,7 @@ def _chk_cuda(*ts):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, aux_z=None, dact_z=None,
          dact=ACT_NONE, aux_grad=False, dact_is_grad=False, pos=None, cls=None, pos_period=0, alpha=1.0, drop_p=0.0,
-         drop_seed=0, drop_offset=0, accumulate=False, split_k=1, block_n=0, cta_group=0):
+         drop_seed=0, drop_offset=0, accumulate=False, split_k=1, block_n=0, cta_group=0, workspace=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_mn/b_mn: operand is stored transposed ([K,M] / [K,N])."""
     _chk_cuda(a, b, out, bias, residual, aux_z, dact_z, pos, cls)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -70,7 +70,10 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
         assert out.dtype == torch.bfloat16
     ep.accumulate = 1 if accumulate else 0
     _lib.call("avt_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
-              C.byref(ep), split_k, block_n, cta_group, _stream())
+              C.byref(ep), split_k, block_n, cta_group, _ptr(workspace),
+              0 if workspace is None else workspace.numel() * workspace.element_size(), _stream())
+    if workspace is not None and split_k > 1:
+        _lib.launch_count += 1
     return out
 
 

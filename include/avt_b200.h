@@ -51,7 +51,11 @@ int avt_set_sm_limit(int n);
  *   if drop_p > 0: v = keep(seed, drop_offset, r * N + c) ? v / (1 - drop_p) : 0
  *   if residual: v += residual[r * ldr + c]
  *   out[r * ldo + c] = out_fp32 ? v : bf16(v)
- * With split_k > 1 the only allowed epilogue is fp32 accumulation into `out` (atomic adds). */
+ * With split_k > 1 the partial sums are combined with fp32 atomics: directly into `out` when the epilogue is a plain
+ * fp32 output (weight gradients; zero-filled first unless `accumulate` is set), otherwise into the
+ * caller's split_k*M*N fp32 `workspace` (one slice per split, plain stores, summed in a fixed order: bit-reproducible),
+ * followed by a small finishing kernel that applies the epilogue (used for the
+ * weight-streaming M <= 128 GEMMs of AVT-h, where one tile per CTA would leave most SMs idle). */
 typedef struct avt_epilogue {
   const float* bias;
   const float* residual;
@@ -85,7 +89,8 @@ typedef struct avt_epilogue {
  * models/future_prediction.py:80-81 encoder/decoder), HF Conv1D (torch.addmm; GPT2Attention.c_attn /
  * c_proj, GPT2MLP.c_fc / c_proj) and their autograd dgrad / wgrad matmuls (func/train.py:222). */
 int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
-                  int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group, void* stream);
+                  int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 
 /* y[r,:] = LayerNorm(x'[r,:]) * gamma + beta over the last dim D (<= 2048, multiple of 4); one warp per row.
  * x' = x, or — residual update fused in — x' = x + add_bf16 (a bf16 branch output), with x' also written to

@@ -130,8 +130,17 @@ def test_gemm_residual_accumulate_splitk():
     ops.gemm(a, b, out, a_mn=True, b_mn=True, accumulate=True)
     _check(out, ref + res.double(), "accumulate")
     out = res.clone()
-    ops.gemm(a, b, out, a_mn=True, b_mn=True, split_k=7)
-    _check(out, ref + res.double(), "split_k")
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, split_k=7, accumulate=True)      # atomics onto the existing values
+    _check(out, ref + res.double(), "split_k accumulate")
+    out = res.clone()
+    ops.gemm(a, b, out, a_mn=True, b_mn=True, split_k=7)                       # overwrite: zero-filled first
+    _check(out, ref, "split_k overwrite")
+    ws = torch.empty(7 * M * N, device="cuda")
+    o1, o2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, o1, a_mn=True, b_mn=True, split_k=7, workspace=ws)          # slices + fixed-order sum
+    ops.gemm(a, b, o2, a_mn=True, b_mn=True, split_k=7, workspace=ws)
+    _check(o1, ref, "split_k slices")
+    assert torch.equal(o1, o2)                                                 # bit-reproducible
 
 
 def test_gemm_pos_cls():
@@ -171,3 +180,37 @@ def test_gemm_dropout_statistics():
     out3 = torch.empty(M, N, device="cuda")
     ops.gemm(a, b, out3, drop_p=p, drop_seed=124, drop_offset=1000)
     assert not torch.equal(out1 != 0, out3 != 0)
+
+
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_gemm_small_m_split_k_two_pass(b_mn):
+    """AVT-h weight-streaming GEMMs (M = 80): split-K partials in an fp32 workspace + finishing epilogue kernel
+    must equal the single-pass fused epilogue."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    M, N, K = 80, 2048, 8192
+    a = _mk((M, K), g)
+    b = _mk((K, N) if b_mn else (N, K), g, 0.02)
+    bias = torch.randn(N, generator=g, device="cuda")
+    ws = torch.empty(8 * M * N, device="cuda")
+    outs = []
+    for sk in (1, 4):
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, b, out, b_mn=b_mn, bias=bias, act=2, aux_z=aux, aux_grad=True, drop_p=0.1, drop_seed=5, drop_offset=7 << 28,
+                 split_k=sk, workspace=ws if sk > 1 else None)
+        outs.append((out.float(), aux.float()))
+    pre = _ref(a, b, False, b_mn) + bias.double()
+    assert ((outs[0][1].double() - outs[1][1].double()).abs() <= 2.0**-7 * outs[0][1].double().abs() + 1e-3).all()
+    kept = (outs[0][0] != 0) & (outs[1][0] != 0)
+    assert torch.equal(outs[0][0] != 0, outs[1][0] != 0)                      # same dropout mask
+    want = _gelu_tanh(pre) / 0.9
+    for o, _ in outs:
+        err = (o.double() - want).abs()[kept]
+        assert (err <= want.abs()[kept] * 2.0**-7 + 2e-3).all()
+    # fp32 output through the TMA-store path (no split) and through the two-pass path
+    o1, o2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, o1, b_mn=b_mn, bias=bias)
+    ops.gemm(a, b, o2, b_mn=b_mn, bias=bias, split_k=8, workspace=ws)
+    _check(o1, pre, "fp32 tma store")
+    _check(o2, pre, "fp32 two-pass")
