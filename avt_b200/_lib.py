@@ -32,6 +32,7 @@ class Epilogue(C.Structure):
         ("drop_p", C.c_float),
         ("drop_seed", C.c_uint64),
         ("drop_offset", C.c_uint64),
+        ("drop_offset_dev", C.c_void_p),
         ("out", C.c_void_p),
         ("ldo", C.c_int64),
         ("out_fp32", C.c_int32),
@@ -51,17 +52,17 @@ SIGNATURES = {
                       _vp],
     "avt_layernorm_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
     "avt_layernorm_bwd": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
-                          _i32, _vp, _i64, _vp],
+                          _vp, _i32, _vp, _i64, _vp],
     "avt_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "avt_patchify_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "avt_colsum_bf16": [_vp, _i64, _i32, _i64, _vp, _vp],
     "avt_frame_sum_grads": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
-    "avt_dropout_apply": [_vp, _i64, _f32, _u64, _u64, _vp, _vp, _vp],
+    "avt_dropout_apply": [_vp, _i64, _f32, _u64, _u64, _vp, _vp, _vp, _vp],
     "avt_sgd_step": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _i32, _i32, _vp],
-    "avt_attention_simt_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp],
+    "avt_attention_simt_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp, _vp],
     "avt_attention_tc_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
     "avt_attention_tc_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
-    "avt_attention_simt_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp],
+    "avt_attention_simt_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp, _vp],
 }
 _SPECIAL = {"avt_abi_version": ([], C.c_int), "avt_last_error": ([], C.c_char_p),
             "avt_layernorm_bwd_workspace_bytes": ([_i64, _i32], C.c_int64)}

@@ -173,9 +173,11 @@ class VisionTransformer(nn.Module):
         dx.zero_()
         dxb.zero_()
         fst = self._aux[("fstat", F)]
+        # only the CLS rows of dx are non-zero here, so their column sums are the last fc2's bias gradient
         ops.layernorm_bwd(dfeats, xcls, fst[0], fst[1], pk.wv("norm.weight"), dx, pk.gv("norm.weight"), pk.gv("norm.bias"),
-                          w["lnws"], dx_bf16=dxb, rows=F, dx_stride=ntok * D, dxb_stride=ntok * D)
-        st.backward(w, dx, dxb)
+                          w["lnws"], dx_bf16=dxb, rows=F, dx_stride=ntok * D, dxb_stride=ntok * D,
+                          dx_colsum=pk.gv(f"blocks.{len(self.blocks) - 1}.mlp.fc2.bias"))
+        st.backward(w, dx, dxb, top_bias_done=True)
         A = self._aux[("patch", M)]
         sk = engine._split_k_for(D, Kp, M, 256)
         ops.gemm(dxb, A, pk.gv("patch_embed.proj.weight").view(D, Kp), a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1)

@@ -107,8 +107,9 @@ __global__ void pos_cls_apply_kernel(const float* __restrict__ s, int period, in
 // y = keep(seed, offset, i) ? x / (1-p) : 0 over a dense [n] tensor (i = linear index); fp32 in, bf16 and/or fp32 out.
 __global__ void __launch_bounds__(256)
 dropout_apply_kernel(const float* __restrict__ x, int64_t n4, float p, uint64_t seed, uint64_t offset,
-                     float* __restrict__ y32, bf16* __restrict__ y16) {
+                     const uint64_t* __restrict__ offset_dev, float* __restrict__ y32, bf16* __restrict__ y16) {
   const float scale = 1.0f / (1.0f - p);
+  if (offset_dev) offset += __ldg(offset_dev);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + g);
@@ -209,14 +210,14 @@ extern "C" int avt_frame_sum_grads(const float* dx, int F, int period, int D, fl
   return AVT_OK;
 }
 
-extern "C" int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* y_f32,
-                                 void* y_bf16, void* stream) {
+extern "C" int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset,
+                                 const uint64_t* offset_dev, float* y_f32, void* y_bf16, void* stream) {
   AVT_REQUIRE(x && (y_f32 || y_bf16), "null pointer");
   AVT_REQUIRE(n % 4 == 0, "n must be a multiple of 4");
   AVT_REQUIRE(p >= 0.f && p < 1.f, "p must be in [0, 1)");
   if (n <= 0) return AVT_OK;
   dropout_apply_kernel<<<grid_for(n / 4, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, n / 4, p, seed, offset, y_f32, reinterpret_cast<bf16*>(y_bf16));
+      x, n / 4, p, seed, offset, offset_dev, y_f32, reinterpret_cast<bf16*>(y_bf16));
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }

@@ -219,6 +219,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+    // CUDA-graph friendly RNG: the per-step part of the Philox offset may live in device memory
+    const uint64_t drop_off = ep.drop_offset + ((ep.drop_p > 0.f && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
     const bool scale_acc = ep.alpha != 1.0f;
     const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte offset (64 B rows)
 
@@ -373,7 +375,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t g0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)col0) >> 2;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t keep = dropout_keep4(ep.drop_seed, ep.drop_offset, g0 + j, ep.drop_p);
+            const uint32_t keep = dropout_keep4(ep.drop_seed, drop_off, g0 + j, ep.drop_p);
             v[2 * j].x = (keep & 1u) ? v[2 * j].x * keep_scale : 0.f;
             v[2 * j].y = (keep & 2u) ? v[2 * j].y * keep_scale : 0.f;
             v[2 * j + 1].x = (keep & 4u) ? v[2 * j + 1].x * keep_scale : 0.f;
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__(256)
 epilogue_apply_kernel(const float* __restrict__ acc, int nslices, int M, int N, const avt_epilogue_t ep) {
   const int64_t total4 = (int64_t)M * N / 4;
   const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+  const uint64_t drop_off = ep.drop_offset + ((ep.drop_p > 0.f && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total4; g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = g * 4;
     const int row = (int)(e0 / N), col = (int)(e0 % N);
@@ -489,7 +492,7 @@ epilogue_apply_kernel(const float* __restrict__ acc, int nslices, int M, int N, 
       for (int j = 0; j < 4; ++j) v[j] *= ep.dact_mode == 1 ? zz[j] : apply_act_grad(ep.dact, zz[j]);
     }
     if (ep.drop_p > 0.f) {
-      const uint32_t keep = dropout_keep4(ep.drop_seed, ep.drop_offset, (uint64_t)g, ep.drop_p);
+      const uint32_t keep = dropout_keep4(ep.drop_seed, drop_off, (uint64_t)g, ep.drop_p);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
     }

@@ -134,6 +134,20 @@ class StackSpec:
     attn_impl: str = "simt"  # "simt" | "tc" (tcgen05 kernel for N=197, hd=64)
 
 
+def _best_split(tiles, kblocks, slots, max_split, unit_overhead):
+    """Split-K factor minimising  waves x (k-blocks per unit + per-unit overhead): a persistent grid of `slots` CTAs (or
+    CTA pairs) runs ceil(units / slots) rounds, so 160 units on 148 SMs cost two rounds, not 1.08."""
+    best_cost, best = None, 1
+    for sk in range(1, max(1, max_split) + 1):
+        kb = -(-kblocks // sk)
+        eff = -(-kblocks // kb)                 # the C-ABI drops empty splits
+        waves = -(-tiles * eff // slots)
+        cost = waves * (kb + unit_overhead)
+        if best_cost is None or cost < best_cost:
+            best_cost, best = cost, eff
+    return best
+
+
 def small_m_split(M, N, K, sms=148):
     """Split-K factor for the weight-streaming GEMMs (M <= 128 rows: one 128 x 64 tile per CTA would leave most SMs
     idle while a few CTAs stream the whole weight matrix). 1 = no split."""
@@ -141,15 +155,15 @@ def small_m_split(M, N, K, sms=148):
         return 1
     tiles = (N + 63) // 64
     kblocks = (K + 63) // 64
-    want = max(1, (sms + tiles - 1) // tiles)
-    return max(1, min(want, kblocks // 4))
+    return _best_split(tiles, kblocks, sms, min(16, kblocks // 2), 6)
 
 
 def _split_k_for(m_w, n_w, k_rows, block_n, sms=148):
-    tiles = ((m_w + 127) // 128) * ((n_w + block_n - 1) // block_n)
+    """Split-K factor for a weight gradient dW[m_w, n_w] contracted over k_rows activations rows (256 x block_n tiles on
+    CTA pairs; the partial sums meet in fp32 atomics, so fewer splits win ties)."""
+    tiles = ((m_w + 255) // 256) * ((n_w + block_n - 1) // block_n)
     kblocks = (k_rows + 63) // 64
-    want = max(1, (2 * sms + tiles - 1) // tiles)
-    return max(1, min(want, max(1, kblocks // 8)))
+    return _best_split(tiles, kblocks, sms // 2, min(32, kblocks // 8), 8)
 
 
 class BlockStack:
@@ -240,7 +254,7 @@ class BlockStack:
         D = s.dim
         hd = D // s.heads
         scale = hd ** -0.5
-        seed, off = rng
+        seed, off, off_dev = (tuple(rng) + (None,))[:3]   # off_dev: device-resident part of the Philox offset (CUDA graphs)
         p_attn = s.p_attn if dropout else 0.0
         p_res = s.p_resid if dropout else 0.0
         y = w["y"]
@@ -255,48 +269,53 @@ class BlockStack:
             else:   # x_in = x_mid(prev) + mlp branch(prev), fused with this layer's LN1
                 ops.layernorm_fwd(xprev, g1, b1, s.eps, w["ln1"][j], st[0], st[1], add=y, x_out=xin)
             self._fwd(w["ln1"][j], nm["qkv"] + ".weight", w["qkv"][j], bias=pk.wv(nm["qkv"] + ".bias"))
-            self._attn_fwd(w["qkv"][j], w["att"][j], w["lse"][j], nb, ntok, hd, scale, p_attn, seed, off + (4 * i << 28))
+            self._attn_fwd(w["qkv"][j], w["att"][j], w["lse"][j], nb, ntok, hd, scale, p_attn, seed, off + (4 * i << 28),
+                           off_dev)
             self._fwd(w["att"][j], nm["proj"] + ".weight", y, bias=pk.wv(nm["proj"] + ".bias"),
-                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 1) << 28))
+                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 1) << 28), drop_offset_dev=off_dev)
             ops.layernorm_fwd(xin, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3],
                               add=y, x_out=xmid)
             # fc1 epilogue writes gelu(z) and gelu'(z): backward only multiplies
             self._fwd(w["ln2"][j], nm["fc1"] + ".weight", w["h"][j], bias=pk.wv(nm["fc1"] + ".bias"), act=s.act,
                       aux_z=w["z"][j] if train else None, aux_grad=True)
             self._fwd(w["h"][j], nm["fc2"] + ".weight", y, bias=pk.wv(nm["fc2"] + ".bias"),
-                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 2) << 28))
-        w["rng"] = (seed, off, p_attn, p_res)
+                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 2) << 28), drop_offset_dev=off_dev)
+        w["rng"] = (seed, off, off_dev, p_attn, p_res)
         w["dims"] = (nb, ntok)
         return self._xbuf(w, train, 2 * s.layers - 1), y
 
-    def _attn_fwd(self, qkv, out, lse, nb, ntok, hd, scale, p, seed, off):
+    def _attn_fwd(self, qkv, out, lse, nb, ntok, hd, scale, p, seed, off, off_dev=None):
         s = self.s
         if s.attn_impl == "tc" and p == 0.0 and not s.causal and hd == 64 and ntok <= 208:
             ops.attention_tc_fwd(qkv, out, lse, nb, s.heads, ntok, scale=scale)
         else:
             ops.attention_simt_fwd(qkv, out, lse, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
-                                   seed=seed, offset=off)
+                                   seed=seed, offset=off, offset_dev=off_dev)
 
-    def _attn_bwd(self, qkv, att, dout, lse, dqkv, nb, ntok, hd, scale, p, seed, off):
+    def _attn_bwd(self, qkv, att, dout, lse, dqkv, nb, ntok, hd, scale, p, seed, off, off_dev=None):
         s = self.s
         if s.attn_impl == "tc" and p == 0.0 and not s.causal and hd == 64 and ntok <= 208:
             ops.attention_tc_bwd(qkv, att, dout, lse, dqkv, nb, s.heads, ntok, scale=scale)
         else:
-            ops.attention_simt_bwd(qkv, dout, lse, dqkv, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
-                                   seed=seed, offset=off)
+            ops.attention_simt_bwd(qkv, att, dout, lse, dqkv, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
+                                   seed=seed, offset=off, offset_dev=off_dev)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, w, dx, dxb):
+    def backward(self, w, dx, dxb, top_bias_done=False):
         """dx fp32 [M, D] / dxb bf16 copy: gradient w.r.t. the stack output (updated in place to the gradient
         w.r.t. the stack input). Parameter gradients are written into pack.g: matrices are overwritten
         (or atomically accumulated by split-K units), biases are accumulated by atomics - the caller zeroes
-        the corresponding region of pack.g first (zero_all_grads / zero_small_grads)."""
+        the corresponding region of pack.g first (zero_all_grads / zero_small_grads). top_bias_done: the caller's own
+        LayerNorm backward already produced the last layer's fc2 bias gradient (column sums of dx)."""
         s, pk = self.s, self.pack
         M, D = dx.shape
         nb, ntok = w["dims"]
-        seed, off, p_attn, p_res = w["rng"]
+        seed, off, off_dev, p_attn, p_res = w["rng"]
         hd = D // s.heads
         scale = hd ** -0.5
+        # Without residual dropout the gradient of a branch's closing Linear output IS the residual-stream gradient, so
+        # its bias gradient (column sums of dx) comes out of the LayerNorm backward that produced dx: no extra pass.
+        fuse_bias = p_res == 0.0
         for i in reversed(range(s.layers)):
             nm = {k: v.format(i=i) for k, v in s.names.items()}
             st = w["st"][i]
@@ -305,26 +324,29 @@ class BlockStack:
             g = dxb
             if p_res > 0.0:
                 g = w["g"]
-                ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 2) << 28), y_bf16=g)
-            self._wgrad(w["h"][i], g, nm["fc2"] + ".weight", nm["fc2"] + ".bias")
+                ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 2) << 28), y_bf16=g, offset_dev=off_dev)
+            self._wgrad(w["h"][i], g, nm["fc2"] + ".weight",
+                        None if fuse_bias and (i < s.layers - 1 or top_bias_done) else nm["fc2"] + ".bias")
             self._dgrad(g, nm["fc2"] + ".weight", w["dz"], dact_z=w["z"][i], dact=s.act, dact_is_grad=True)
             self._wgrad(w["ln2"][i], w["dz"], nm["fc1"] + ".weight", nm["fc1"] + ".bias")
             self._dgrad(w["dz"], nm["fc1"] + ".weight", w["dln"])
             ops.layernorm_bwd(w["dln"], xmid, st[2], st[3], pk.wv(nm["ln2"] + ".weight"), dx,
-                              pk.gv(nm["ln2"] + ".weight"), pk.gv(nm["ln2"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb)
+                              pk.gv(nm["ln2"] + ".weight"), pk.gv(nm["ln2"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb,
+                              dx_colsum=pk.gv(nm["proj"] + ".bias") if fuse_bias else None)
             # ---- attention branch: x_mid = x_in + drop(proj(attn(qkv(LN1(x_in)))))
             g = dxb
             if p_res > 0.0:
                 g = w["g"]
-                ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 1) << 28), y_bf16=g)
-            self._wgrad(w["att"][i], g, nm["proj"] + ".weight", nm["proj"] + ".bias")
+                ops.dropout_apply(dx, p_res, seed, off + ((4 * i + 1) << 28), y_bf16=g, offset_dev=off_dev)
+            self._wgrad(w["att"][i], g, nm["proj"] + ".weight", None if fuse_bias else nm["proj"] + ".bias")
             self._dgrad(g, nm["proj"] + ".weight", w["datt"])
             self._attn_bwd(w["qkv"][i], w["att"][i], w["datt"], w["lse"][i], w["dqkv"], nb, ntok, hd, scale, p_attn, seed,
-                           off + (4 * i << 28))
+                           off + (4 * i << 28), off_dev)
             self._wgrad(w["ln1"][i], w["dqkv"], nm["qkv"] + ".weight", nm["qkv"] + ".bias")
             self._dgrad(w["dqkv"], nm["qkv"] + ".weight", w["dln"])
             ops.layernorm_bwd(w["dln"], xin, st[0], st[1], pk.wv(nm["ln1"] + ".weight"), dx,
-                              pk.gv(nm["ln1"] + ".weight"), pk.gv(nm["ln1"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb)
+                              pk.gv(nm["ln1"] + ".weight"), pk.gv(nm["ln1"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb,
+                              dx_colsum=pk.gv(s.names["fc2"].format(i=i - 1) + ".bias") if fuse_bias and i > 0 else None)
             if self.layer_done_hook is not None:
                 self.layer_done_hook(i)
         return dx, dxb

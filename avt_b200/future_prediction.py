@@ -137,7 +137,7 @@ class AVTh(nn.Module):
         self._grads_ready_hook = None
         self._pack = None
         self._stack = None
-        self._step = 0
+        self._rng_dev = None
         self._aux = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -178,28 +178,35 @@ class AVTh(nn.Module):
                                   gb=torch.empty(M, Dh, dtype=torch.bfloat16, device=dev),
                                   fsum=torch.empty(T * Dh, dtype=torch.float32, device=dev))
         a = self._aux[key]
-        self._step += 1
+        # Philox stream: seed from torch's global seed; the per-step offset lives in DEVICE memory and is advanced by a
+        # (capturable) in-place add, so a CUDA-graph replay of the step draws fresh dropout masks. Each forward keeps
+        # its own snapshot for its backward.
         seed = (torch.initial_seed() ^ 0x5DEECE66D) & 0xFFFFFFFFFFFF
-        off = (self._step & 0xFFFFFF) << 38
+        off, off_dev = 0, None
+        if drop:
+            if self._rng_dev is None or self._rng_dev.device != dev:
+                self._rng_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._rng_dev.add_(1 << 38)
+            off_dev = self._rng_dev.clone()
         p_embd = self.embd_pdrop if drop else 0.0
         ops.cast_bf16(feats2d.contiguous().float(), a["xb"])
         # h0 = dropout(encoder(feats) + wpe[0:T])   (reference :163 + HF GPT2Model.forward)
         sk = engine.small_m_split(M, Dh, C)
         ops.gemm(a["xb"], pk.bv("encoder.weight"), w["x"][0], pos=pk.wv("gpt_model.wpe.weight")[:T], pos_period=T,
-                 drop_p=p_embd, drop_seed=seed, drop_offset=off + (255 << 28), split_k=sk,
+                 drop_p=p_embd, drop_seed=seed, drop_offset=off + (255 << 28), drop_offset_dev=off_dev, split_k=sk,
                  workspace=st._gemm_ws(w["x"][0], sk))
-        xmid, y = st.forward(w, B, T, train_graph, rng=(seed, off), dropout=drop)
+        xmid, y = st.forward(w, B, T, train_graph, rng=(seed, off, off_dev), dropout=drop)
         xf = st._xbuf(w, train_graph, 2 * self.n_layer)
         ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, a["lnf"],
                           a["fst"][0], a["fst"][1], add=y, x_out=xf)
         decoded = torch.empty(M, C, dtype=torch.float32, device=dev)
         sk = engine.small_m_split(M, C, Dh)
         ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded, split_k=sk, workspace=st._gemm_ws(decoded, sk))
-        return decoded, (w, xf, B, T, p_embd, seed, off)
+        return decoded, (w, xf, B, T, p_embd, seed, off, off_dev)
 
     def _run_backward(self, saved, ddec):
         pk, st = self._pack, self._stack
-        w, xf, B, T, p_embd, seed, off = saved
+        w, xf, B, T, p_embd, seed, off, off_dev = saved
         M, C, Dh = B * T, self.in_features, self.inter_dim
         a = self._aux[("io", M)]
         pk.zero_small_grads()
@@ -215,7 +222,7 @@ class AVTh(nn.Module):
         g32, gb = dx, dxb
         if p_embd > 0.0:
             g32, gb = a["g32"], a["gb"]
-            ops.dropout_apply(dx, p_embd, seed, off + (255 << 28), y_f32=g32, y_bf16=gb)
+            ops.dropout_apply(dx, p_embd, seed, off + (255 << 28), y_f32=g32, y_bf16=gb, offset_dev=off_dev)
         ops.frame_sum_grads(g32, B, T, Dh, a["fsum"], dpos=pk.gv("gpt_model.wpe.weight")[:T], accumulate=False)
         ops.gemm(gb, a["xb"], pk.gv("encoder.weight"), a_mn=True, b_mn=True)                 # dWenc = g^T feats
         dfeats = torch.empty(M, C, dtype=torch.float32, device=ddec.device)

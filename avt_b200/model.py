@@ -48,11 +48,19 @@ class AVTModel(nn.Module):
         return out, losses
 
 
-def training_loss(outputs, aux_losses, target, target_subclips):
+def past_targets(target_subclips):
+    """Per-frame label of the past-prediction loss: the mode over the sub-clip's frame labels
+    (func/train_eval_ops.py:70-75). Label preparation only — kept out of the graph-captured part of the step because
+    torch.mode synchronises."""
+    return torch.mode(target_subclips, -1)[0]
+
+
+def training_loss(outputs, aux_losses, target, target_subclips=None, past_tgt=None):
     """sum_k mean(loss_k), weights 1/1/1: CE(future), CE(past vs per-frame mode label, ignore_index -1), MSE feat
     (func/train_eval_ops.py:57-85, loss_fn/multidim_xentropy.py:10-25, func/train.py:207-217, expts/01:1-2)."""
     losses = {"cls_action": F.cross_entropy(outputs["logits/action"], target, ignore_index=-1, reduction="none")}
-    past_tgt = torch.mode(target_subclips, -1)[0]
+    if past_tgt is None:
+        past_tgt = past_targets(target_subclips)
     pl = outputs["past_logits/action"]
     losses["past_cls_action"] = F.cross_entropy(pl.flatten(0, 1), past_tgt.flatten(), ignore_index=-1,
                                                 reduction="none").view(past_tgt.shape)

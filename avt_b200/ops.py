@@ -26,7 +26,8 @@ def _chk_cuda(*ts):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, aux_z=None, dact_z=None,
          dact=ACT_NONE, aux_grad=False, dact_is_grad=False, pos=None, cls=None, pos_period=0, alpha=1.0, drop_p=0.0,
-         drop_seed=0, drop_offset=0, accumulate=False, split_k=1, block_n=0, cta_group=0, workspace=None):
+         drop_seed=0, drop_offset=0, drop_offset_dev=None, accumulate=False, split_k=1, block_n=0, cta_group=0,
+         workspace=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_mn/b_mn: operand is stored transposed ([K,M] / [K,N])."""
     _chk_cuda(a, b, out, bias, residual, aux_z, dact_z, pos, cls)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -63,6 +64,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
     ep.drop_p = drop_p
     ep.drop_seed = drop_seed
     ep.drop_offset = drop_offset
+    ep.drop_offset_dev = _ptr(drop_offset_dev)
     ep.out = _ptr(out)
     ep.ldo = out.stride(0)
     ep.out_fp32 = 1 if out.dtype == torch.float32 else 0
@@ -102,8 +104,10 @@ def layernorm_bwd_workspace(rows, D):
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace, *, dx_in=None, dx_bf16=None, rows=None,
-                  x_stride=None, dx_stride=None, dxb_stride=None, accumulate=False):
-    _chk_cuda(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace)
+                  x_stride=None, dx_stride=None, dxb_stride=None, accumulate=False, dx_colsum=None):
+    """dx_colsum (fp32 [D], optional) receives the column sums of dx_out (= bias gradient of the Linear that produced
+    this residual stream update)."""
+    _chk_cuda(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace, dx_colsum)
     D = gamma.numel()
     rows = dy.shape[0] if rows is None else rows
     x_stride = x.stride(0) if x_stride is None else x_stride
@@ -112,7 +116,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace, *,
         dxb_stride = dx_bf16.stride(0)
     _lib.call("avt_layernorm_bwd", _ptr(dy), int(dy.dtype == torch.float32), dy.stride(0), _ptr(x), x_stride, _ptr(mean),
               _ptr(rstd), _ptr(gamma), rows, D, _ptr(dx_in), _ptr(dx_out), dx_stride, _ptr(dx_bf16), dxb_stride or 0,
-              _ptr(dgamma), _ptr(dbeta), int(accumulate), _ptr(workspace), workspace.numel() * workspace.element_size(),
+              _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum), int(accumulate), _ptr(workspace),
+              workspace.numel() * workspace.element_size(),
               _stream())
 
 
@@ -147,24 +152,27 @@ def frame_sum_grads(dx, F, period, D, workspace, dpos=None, dcls=None, dbias=Non
               _ptr(workspace), _stream())
 
 
-def dropout_apply(x, p, seed, offset, y_f32=None, y_bf16=None):
+def dropout_apply(x, p, seed, offset, y_f32=None, y_bf16=None, offset_dev=None):
     _chk_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
-    _lib.call("avt_dropout_apply", _ptr(x), x.numel(), float(p), int(seed), int(offset), _ptr(y_f32), _ptr(y_bf16), _stream())
+    _lib.call("avt_dropout_apply", _ptr(x), x.numel(), float(p), int(seed), int(offset), _ptr(offset_dev), _ptr(y_f32),
+              _ptr(y_bf16), _stream())
 
 
-def attention_simt_fwd(qkv, out, lse, B, H, N, hd, *, causal, scale, drop_p=0.0, seed=0, offset=0):
+def attention_simt_fwd(qkv, out, lse, B, H, N, hd, *, causal, scale, drop_p=0.0, seed=0, offset=0, offset_dev=None):
     _chk_cuda(qkv, out, lse)
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
     _lib.call("avt_attention_simt_fwd", _ptr(qkv), _ptr(out), _ptr(lse), B, H, N, hd, int(causal), float(scale),
-              float(drop_p), int(seed), int(offset), _stream())
+              float(drop_p), int(seed), int(offset), _ptr(offset_dev), _stream())
 
 
-def attention_simt_bwd(qkv, dout, lse, dqkv, B, H, N, hd, *, causal, scale, drop_p=0.0, seed=0, offset=0):
-    _chk_cuda(qkv, dout, lse, dqkv)
+def attention_simt_bwd(qkv, out, dout, lse, dqkv, B, H, N, hd, *, causal, scale, drop_p=0.0, seed=0, offset=0,
+                       offset_dev=None):
+    _chk_cuda(qkv, out, dout, lse, dqkv)
     assert dout.dtype == torch.bfloat16 and dqkv.dtype == torch.bfloat16 and dout.is_contiguous() and dqkv.is_contiguous()
-    _lib.call("avt_attention_simt_bwd", _ptr(qkv), _ptr(dout), _ptr(lse), _ptr(dqkv), B, H, N, hd, int(causal),
-              float(scale), float(drop_p), int(seed), int(offset), _stream())
+    assert out.dtype == torch.bfloat16 and out.is_contiguous()
+    _lib.call("avt_attention_simt_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), B, H, N, hd, int(causal),
+              float(scale), float(drop_p), int(seed), int(offset), _ptr(offset_dev), _stream())
 
 
 def attention_tc_fwd(qkv, out, lse, F, H, N, *, scale):

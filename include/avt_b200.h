@@ -48,7 +48,9 @@ int avt_set_sm_limit(int n);
  *   if dact_z:  v *= (dact_mode == 1 ? dact_z[r * ldz + c] : dact'(dact_z[r * ldz + c]))
  *               (backward through the activation: dact_z holds either the pre-activation, differentiated here
  *                with kind `dact`, or the derivative itself as saved by a forward with aux_mode = 1)
- *   if drop_p > 0: v = keep(seed, drop_offset, r * N + c) ? v / (1 - drop_p) : 0
+ *   if drop_p > 0: v = keep(seed, drop_offset [+ *drop_offset_dev], r * N + c) ? v / (1 - drop_p) : 0
+ *               (drop_offset_dev: optional device-resident part of the Philox offset, so that a captured CUDA graph
+ *                draws a fresh mask on every replay)
  *   if residual: v += residual[r * ldr + c]
  *   out[r * ldo + c] = out_fp32 ? v : bf16(v)
  * With split_k > 1 the partial sums are combined with fp32 atomics: directly into `out` when the epilogue is a plain
@@ -74,6 +76,7 @@ typedef struct avt_epilogue {
   float drop_p;
   uint64_t drop_seed;
   uint64_t drop_offset;
+  const uint64_t* drop_offset_dev; /* device pointer or NULL */
   void* out;
   int64_t ldo;
   int32_t out_fp32;
@@ -105,14 +108,18 @@ int avt_layernorm_fwd(const float* x, int64_t x_stride, const void* add_bf16, in
                       int y_fp32, int64_t y_stride, float* mean, float* rstd, void* stream);
 
 /* LayerNorm backward. dx_out = (dx_in ? dx_in : 0) + dLN(dy); optional bf16 copy of dx_out (the A operand
- * of the next dgrad / wgrad GEMM); dgamma / dbeta are overwritten or accumulated. `workspace` must hold
- * avt_layernorm_bwd_workspace_bytes(rows, D) bytes. Replaces autograd of torch.nn.LayerNorm + the
- * residual-branch gradient add. */
+ * of the next dgrad / wgrad GEMM); dgamma / dbeta are overwritten or accumulated. dx_colsum ([D], may be NULL)
+ * receives the column sums of dx_out: dx_out is the gradient of the residual stream, i.e. of the output of the
+ * Linear that closed the previous residual branch (timm Attention.proj / Mlp.fc2), so this IS that layer's bias
+ * gradient and the separate reduction pass over [rows, D] disappears. `workspace` must hold
+ * avt_layernorm_bwd_workspace_bytes(rows, D) bytes. Large row counts stream through a per-warp shared-memory
+ * ring filled by bulk async copies; <= 2 x SM-count rows use one CTA per row. Replaces autograd of
+ * torch.nn.LayerNorm + the residual-branch gradient add. */
 int64_t avt_layernorm_bwd_workspace_bytes(int64_t rows, int D);
 int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride, const float* x, int64_t x_stride,
                       const float* mean, const float* rstd, const float* gamma, int64_t rows, int D, const float* dx_in,
                       float* dx_out, int64_t dx_stride, void* dx_bf16, int64_t dxb_stride, float* dgamma, float* dbeta,
-                      int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+                      float* dx_colsum, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* dst[i] = bf16(src[i]), i < n (weight down-cast of the fp32 master parameters). */
 int avt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
@@ -134,9 +141,10 @@ int avt_frame_sum_grads(const float* dx, int F, int period, int D, float* dpos, 
 
 /* y = keep(seed, offset, i) ? x[i] / (1-p) : 0 over a dense tensor of n (multiple of 4) elements; the same
  * (seed, offset) reproduces the mask a GEMM epilogue applied to a dense [M, N] output (i = r*N + c).
- * Backward of torch.nn.Dropout (HF embd / resid dropout). Either output may be NULL. */
-int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* y_f32, void* y_bf16,
-                      void* stream);
+ * Backward of torch.nn.Dropout (HF embd / resid dropout). Either output may be NULL. offset_dev (device pointer,
+ * may be NULL) is added to `offset`, as for avt_epilogue_t.drop_offset_dev. */
+int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                      float* y_f32, void* y_bf16, void* stream);
 
 /* Multi-head attention on CUDA cores for short sequences / wide heads (AVT-h: T <= 16, head_dim 256..1024).
  * qkv bf16 [B*N, 3*H*hd], column = s*H*hd + h*hd + d (timm Attention.qkv and HF c_attn packing);
@@ -145,9 +153,11 @@ int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t seed, uint64_
  * Replaces HF GPT2Attention._attn (matmul, /sqrt(hd), causal mask, softmax, attn_dropout, matmul) and its
  * autograd backward; also usable for timm Attention (N = 197, hd = 64, causal = 0). */
 int avt_attention_simt_fwd(const void* qkv, void* out, float* lse, int B, int H, int N, int hd, int causal, float scale,
-                           float drop_p, uint64_t seed, uint64_t offset, void* stream);
-int avt_attention_simt_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, int B, int H, int N, int hd,
-                           int causal, float scale, float drop_p, uint64_t seed, uint64_t offset, void* stream);
+                           float drop_p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+/* Backward: `out` is the forward output (delta_i = dO_i . O_i, so query-row and key-row work items are independent). */
+int avt_attention_simt_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H,
+                           int N, int hd, int causal, float scale, float drop_p, uint64_t seed, uint64_t offset,
+                           const uint64_t* offset_dev, void* stream);
 
 /* ViT spatial attention on tcgen05 tensor cores: out = softmax(Q K^T * scale) V per (frame, head), for
  * N <= 208 tokens per frame and head_dim 64 (ViT-B/16, ViT-L/16: N = 197). Same qkv / out / lse layout as

@@ -47,7 +47,7 @@ def test_attention_tc_bwd(F, H, N):
         ref = qd.grad
     else:             # full size: the CUDA-core kernel (itself checked against fp64 above) is the reference
         ref = torch.empty_like(dqkv)
-        ops.attention_simt_bwd(qkv, dout, lse, ref, F, H, N, 64, causal=False, scale=0.125)
+        ops.attention_simt_bwd(qkv, out, dout, lse, ref, F, H, N, 64, causal=False, scale=0.125)
     for s, name in enumerate(("dq", "dk", "dv")):
         r = rel(dqkv[:, s * D:(s + 1) * D], ref[:, s * D:(s + 1) * D])
         # P, dS rounded to bf16 for the MMAs + bf16 storage of the result (+ bf16 reference at full size)

@@ -77,10 +77,20 @@ def test_avth_interface_matches_reference_names_and_errors():
 
 
 def test_split_k_heuristic():
-    from avt_b200.engine import _split_k_for
-    assert _split_k_for(3072, 768, 15760, 256) >= 4      # 72 output tiles on 148 SMs -> split the 15760-row contraction
+    """Wave-aware split-K: units = tiles x split must not spill a few units into an extra round of the persistent grid."""
+    from avt_b200.engine import _best_split, _split_k_for, small_m_split
+    sk = _split_k_for(3072, 768, 15760, 256)             # 36 pair tiles on 74 CTA pairs -> split the 15760-row contraction
+    assert sk >= 2 and (36 * sk) % 74 in (0, *range(60, 74))   # last round at least ~80 % full
     assert _split_k_for(2048, 8192, 80, 256) == 1        # AVT-h wgrad: K = 80 rows, nothing to split
     assert _split_k_for(768, 768, 15760, 256) <= 31
+    # AVT-h weight-streaming GEMMs (M = 80): 96 / 32 / 128 / 32 tiles of 64 columns on 148 SMs
+    for N, K in [(6144, 2048), (2048, 2048), (8192, 2048), (2048, 8192)]:
+        s = small_m_split(80, N, K)
+        units = (N // 64) * s
+        waves = -(-units // 148)
+        assert units / (waves * 148) >= 0.8, (N, K, s)
+    assert small_m_split(15760, 768, 768) == 1
+    assert _best_split(10, 4, 148, 1, 6) == 1
 
 
 def _dp_worker(rank, world, port, q):

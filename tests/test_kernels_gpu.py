@@ -28,7 +28,11 @@ def assert_bf16_close(out, ref, what="", ulps=1.0, floor=1e-3):
     assert (err <= tol).all(), f"{what}: max err {err.max().item():.3e}, worst ratio {(err / tol).max().item():.2f}"
 
 
-@pytest.mark.parametrize("rows,D,eps", [(80 * 197, 768, 1e-6), (80, 2048, 1e-5), (33, 64, 1e-6), (10, 1024, 1e-6), (7, 640, 1e-5)])
+# three backward variants: bulk-async pipelined (many rows, 256 <= D <= 1024), one CTA per row (<= 296 rows),
+# register-resident fallback (everything else)
+@pytest.mark.parametrize("rows,D,eps", [(80 * 197, 768, 1e-6), (80, 2048, 1e-5), (33, 64, 1e-6), (10, 1024, 1e-6), (7, 640, 1e-5),
+                                        (3001, 768, 1e-6), (120 * 197, 1024, 1e-6), (1500, 264, 1e-5), (1000, 64, 1e-6),
+                                        (400, 2048, 1e-5), (297, 512, 1e-6)])
 def test_layernorm_fwd_bwd(rows, D, eps):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(rows + D)
@@ -55,15 +59,21 @@ def test_layernorm_fwd_bwd(rows, D, eps):
     dxb = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
     dg, db = torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
     ws = torch.empty(ops.layernorm_bwd_workspace(rows, D), dtype=torch.uint8, device="cuda")
-    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, ws, dx_in=dres, dx_bf16=dxb)
+    dcol = torch.full((D,), 7.0, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, ws, dx_in=dres, dx_bf16=dxb, dx_colsum=dcol)
     assert rel(dx, xd.grad + dres.double()) < 1e-5
     assert rel(dg, gd.grad) < 1e-5 and rel(db, bd.grad) < 1e-5
+    assert rel(dcol, (xd.grad + dres.double()).sum(0)) < 1e-5       # bias gradient of the branch-closing Linear
     assert_bf16_close(dxb, xd.grad + dres.double(), "ln bwd bf16 copy")
     # accumulate mode + fp32 dy + in-place dx
     dg2, db2 = dg.clone(), db.clone()
     dx2 = dres.clone()
     ops.layernorm_bwd(dy.float(), x, mean, rstd, gamma, dx2, dg2, db2, ws, dx_in=dx2, accumulate=True)
     assert rel(dx2, dx) < 1e-6 and rel(dg2, 2 * dg) < 1e-6 and rel(db2, 2 * db) < 1e-6
+    # no residual gradient (first LayerNorm backward of a chain)
+    dx3 = torch.empty(rows, D, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx3, dg2, db2, ws)
+    assert rel(dx3, xd.grad) < 1e-5 and rel(dg2, dg) < 1e-6
 
 
 def test_layernorm_fused_residual_add():
@@ -181,7 +191,7 @@ def test_attention_simt(B, H, N, hd, causal):
     dout = torch.randn(B * N, D, generator=g, device="cuda").to(torch.bfloat16)
     o_ref.backward(dout.double())
     dqkv = torch.empty_like(qkv)
-    ops.attention_simt_bwd(qkv, dout, lse, dqkv, B, H, N, hd, causal=causal, scale=scale)
+    ops.attention_simt_bwd(qkv, out, dout, lse, dqkv, B, H, N, hd, causal=causal, scale=scale)
     assert rel(dqkv, qd.grad) < 4e-3, rel(dqkv, qd.grad)   # bf16 storage of dq/dk/dv: ~2^-9 rms per element
 
 
@@ -207,7 +217,7 @@ def test_attention_simt_dropout_consistency():
     dout = torch.randn(B * N, D, generator=g, device="cuda").to(torch.bfloat16)
     o_ref.backward(dout.double())
     dqkv = torch.empty_like(qkv)
-    ops.attention_simt_bwd(qkv, dout, lse, dqkv, B, H, N, hd, causal=True, scale=scale, drop_p=p, seed=9, offset=1 << 30)
+    ops.attention_simt_bwd(qkv, out, dout, lse, dqkv, B, H, N, hd, causal=True, scale=scale, drop_p=p, seed=9, offset=1 << 30)
     assert rel(dqkv, qd.grad) < 4e-3
     keep_rate = mask[torch.tril(torch.ones(N, N, dtype=torch.bool, device="cuda")).expand(B, H, N, N)].mean().item()
     assert abs(keep_rate - (1 - p)) < 0.03
