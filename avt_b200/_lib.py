@@ -50,6 +50,8 @@ SIGNATURES = {
     "avt_set_sm_limit": [_i32],
     "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp, _i64,
                       _vp],
+    "avt_gemm_bf16_colsum": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp,
+                             _i64, _vp, _vp],
     "avt_layernorm_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _f32, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
     "avt_layernorm_bwd": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
                           _vp, _i32, _vp, _i64, _vp],

@@ -29,7 +29,8 @@ constexpr int kBM = 128;        // accumulator rows per CTA (UMMA M = 128 per CT
 constexpr int kBK = 64;         // K per smem stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
 constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, each takes half of the tile's columns
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kSumWarps = 2;     // column sums of the A operand (bias gradients fused into the weight-gradient GEMM)
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32 * kSumWarps;
 constexpr int kSlotBytes = 2048;  // TMA-store staging slot: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -53,6 +54,8 @@ struct GemmParams {
   int tma_out;  // `out` (and bf16 aux_z) leave through TMA stores: 1 = bf16 out, 2 = fp32 out (plain overwrite)
   int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
   int split_slices;  // split-K partials go to out + split*M*ldo (deterministic two-pass) instead of atomics
+  int k_rotate;      // producer walks each tile's k-blocks from a tile-dependent start
+  float* a_colsum;   // [M] += sum_k A[m, k] (A MN-major only): the bias gradient when A = dY^T of a weight-gradient GEMM
   avt_epilogue_t ep;
 };
 
@@ -77,7 +80,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue     (every CTA's own copy)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA     (CG=2: the leader's copy)
   uint64_t* tin_bar = tempty_bar + 2;              // [kEpiWarps][2] TMA -> epilogue warp (dact_z staging)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tin_bar + 2 * kEpiWarps);
+  uint64_t* sum_bar = tin_bar + 2 * kEpiWarps;     // [kStages]  MMA -> column-sum warps (stage consumed by the tensor core)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sum_bar + Cfg::kStages);
+  const bool do_colsum = A_MN && p.a_colsum != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,7 +96,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.tma_in) tma_prefetch_desc(&tmIn);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_colsum ? 1 + kSumWarps : 1);   // a stage is free once the MMA and the column-sum warps left it
+      mbar_init(&sum_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -128,7 +134,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * BNL;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
-      for (int kb = kb0; kb < kb1; ++kb) {
+      // weight-streaming GEMMs (M <= 128): every CTA reads the SAME A k-blocks; starting each tile at a different
+      // k offset keeps 100+ SMs from queueing on one L2 slice at the same moment (the sum order is irrelevant)
+      const int nkb = kb1 - kb0;
+      const int rot = p.k_rotate ? (tile * 5) % nkb : 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb0 + (i + rot >= nkb ? i + rot - nkb : i + rot);
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
@@ -191,9 +202,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if constexpr (CG == 2) {
               umma_commit_pair(&empty_bar[stage], 3);                    // smem slot free in both CTAs
+              if (do_colsum) umma_commit_pair(&sum_bar[stage], 3);
               if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc], 3);   // accumulator complete in both CTAs
             } else {
               umma_commit(&empty_bar[stage]);
+              if (do_colsum) umma_commit(&sum_bar[stage]);
               if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
             }
           }
@@ -202,6 +215,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 2 + kEpiWarps) {
+    // ============================== column sums of A (warps 10..11; weight-gradient GEMMs with a bias) ==============
+    // A = dY^T arrives MN-major: per stage two [64 k][64 m] boxes, 128-byte rows, SWIZZLE_128B. The MMA's commit on
+    // sum_bar says the tensor core is done with the stage (so the bytes are there); these warps add the 64 k-rows of
+    // every m column of the n-tile-0 units into registers, then release the stage. The reduction over the 15 760
+    // activation rows rides on operand bytes that are in shared memory anyway: no separate pass over dY in HBM.
+    if constexpr (A_MN) {
+      if (do_colsum) {
+        const int t = threadIdx.x - 32 * (2 + kEpiWarps);     // 0..63
+        const int chunk = t & 15;                              // 8 m values (16 bytes): box = chunk / 8
+        const int kgrp = t >> 4;                               // 16 k rows each
+        const uint32_t box_off = (chunk >> 3) * 8192;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = unit0; unit < num_units; unit += unit_stride) {
+          const int tile = unit / p.split_k, split = unit % p.split_k;
+          const bool mine = (tile % p.num_n_tiles) == 0;
+          const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
+          const int kb0 = split * p.kb_per_split;
+          const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+          float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&sum_bar[stage], phase);
+            if (mine) {
+              const uint8_t* sA = smem + stage * Cfg::kStageBytes + box_off;
+#pragma unroll 4
+              for (int r = 0; r < 16; ++r) {
+                const int row = kgrp * 16 + r;
+                const uint4 v = *reinterpret_cast<const uint4*>(sA + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
+                acc8[0] += bf16_lo(v.x); acc8[1] += bf16_hi(v.x); acc8[2] += bf16_lo(v.y); acc8[3] += bf16_hi(v.y);
+                acc8[4] += bf16_lo(v.z); acc8[5] += bf16_hi(v.z); acc8[6] += bf16_lo(v.w); acc8[7] += bf16_hi(v.w);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+          if (mine) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // the four k-groups of a column meet in a shuffle, then one atomic per column
+              float v = acc8[j];
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              const int m = m0 + chunk * 8 + j;
+              if (lane < 16 && m < p.M) atomicAdd(p.a_colsum + m, v);
+            }
+          }
+        }
       }
     }
   } else {
@@ -611,6 +673,13 @@ using namespace avt;
 extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M,
                              int64_t N, int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group,
                              void* workspace, int64_t workspace_bytes, void* stream) {
+  return avt_gemm_bf16_colsum(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, split_k, block_n, cta_group, workspace,
+                              workspace_bytes, nullptr, stream);
+}
+
+extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M,
+                                    int64_t N, int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group,
+                                    void* workspace, int64_t workspace_bytes, float* a_colsum, void* stream) {
   AVT_REQUIRE(A && B && ep && ep->out, "null pointer");
   AVT_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
   AVT_REQUIRE(N % 32 == 0, "N must be a multiple of 32");
@@ -636,7 +705,10 @@ extern "C" int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B
   if (ep->residual) AVT_REQUIRE(ep->ldr % 4 == 0, "residual ld must be a multiple of 4");
   if (ep->aux_z || ep->dact_z) AVT_REQUIRE(ep->ldz % 8 == 0, "z ld must be a multiple of 8");
 
+  AVT_REQUIRE(!a_colsum || a_mn, "a_colsum needs the A operand stored transposed (a_mn = 1: A = dY^T of a weight gradient)");
   GemmParams p;
+  p.a_colsum = a_colsum;
+  p.k_rotate = M <= 128 ? 1 : 0;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.num_m_tiles = (int)((M + kBM * cta_group - 1) / (kBM * cta_group));
   p.num_n_tiles = (int)((N + block_n - 1) / block_n);

@@ -153,7 +153,8 @@ def small_m_split(M, N, K, sms=148):
     idle while a few CTAs stream the whole weight matrix). 1 = no split."""
     if M > 128:
         return 1
-    tiles = (N + 63) // 64
+    bn = ops.small_m_block_n(N)
+    tiles = (N + bn - 1) // bn
     kblocks = (K + 63) // 64
     return _best_split(tiles, kblocks, sms, min(16, kblocks // 2), 6)
 
@@ -203,9 +204,11 @@ class BlockStack:
         if self.s.conv1d:   # dW[in, out] = X^T dY
             sk = _split_k_for(x.shape[1], dy.shape[1], rows, 256)
             ops.gemm(x, dy, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed)
-        else:               # dW[out, in] = dY^T X
+        else:               # dW[out, in] = dY^T X; the bias gradient (column sums of dY) rides on the A tiles in smem
             sk = _split_k_for(dy.shape[1], x.shape[1], rows, 256)
-            ops.gemm(dy, x, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed)
+            ops.gemm(dy, x, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed,
+                     a_colsum=self.pack.gv(bname) if bname is not None else None)
+            return
         if bname is not None:
             ops.colsum(dy, self.pack.gv(bname))
 

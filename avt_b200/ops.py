@@ -24,11 +24,18 @@ def _chk_cuda(*ts):
             raise RuntimeError("avt_b200 ops need CUDA tensors (there is no CPU path)")
 
 
+def small_m_block_n(N):
+    """Tile width of the weight-streaming GEMMs (AVT-h, M = B*T <= 128 rows). Measured on B200 (tools/sweep.py head):
+    128-wide tiles (256-byte weight rows per TMA box) + split-K beat 64-wide ones once N >= 2048."""
+    return 128 if N >= 2048 else 64
+
+
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, aux_z=None, dact_z=None,
          dact=ACT_NONE, aux_grad=False, dact_is_grad=False, pos=None, cls=None, pos_period=0, alpha=1.0, drop_p=0.0,
          drop_seed=0, drop_offset=0, drop_offset_dev=None, accumulate=False, split_k=1, block_n=0, cta_group=0,
-         workspace=None):
-    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_mn/b_mn: operand is stored transposed ([K,M] / [K,N])."""
+         workspace=None, a_colsum=None):
+    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_mn/b_mn: operand is stored transposed ([K,M] / [K,N]).
+    a_colsum (fp32 [M], needs a_mn): += sum_k A[m, k], the bias gradient when A = dY^T of a weight-gradient GEMM."""
     _chk_cuda(a, b, out, bias, residual, aux_z, dact_z, pos, cls)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
@@ -44,7 +51,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
     assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
     assert tuple(out.shape) == (M, N), (out.shape, M, N)
     if block_n == 0 and M <= 128:
-        block_n = 64          # weight-streaming GEMMs (AVT-h, M = B*T rows): more, narrower tiles -> more SMs pulling HBM
+        block_n = small_m_block_n(N)
     ep = Epilogue()
     ep.bias = _ptr(bias)
     ep.residual = _ptr(residual)
@@ -71,9 +78,15 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
     if not ep.out_fp32:
         assert out.dtype == torch.bfloat16
     ep.accumulate = 1 if accumulate else 0
-    _lib.call("avt_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
-              C.byref(ep), split_k, block_n, cta_group, _ptr(workspace),
-              0 if workspace is None else workspace.numel() * workspace.element_size(), _stream())
+    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    if a_colsum is None:
+        _lib.call("avt_gemm_bf16", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
+                  C.byref(ep), split_k, block_n, cta_group, _ptr(workspace), ws_bytes, _stream())
+    else:
+        _chk_cuda(a_colsum)
+        assert a_mn and a_colsum.dtype == torch.float32 and a_colsum.numel() == M
+        _lib.call("avt_gemm_bf16_colsum", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
+                  C.byref(ep), split_k, block_n, cta_group, _ptr(workspace), ws_bytes, _ptr(a_colsum), _stream())
     if workspace is not None and split_k > 1:
         _lib.launch_count += 1
     return out

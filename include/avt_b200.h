@@ -95,6 +95,15 @@ int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t l
                   int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* Same GEMM, plus a_colsum[m] += sum_k A[m, k] (fp32 [M], atomics; NULL = off). Requires a_mn = 1. In a weight-gradient
+ * GEMM dW = dY^T X the A operand is dY^T, so a_colsum is the bias gradient (column sums of dY): two extra warps add up
+ * the A tiles that are in shared memory for the tensor core anyway, and the separate avt_colsum_bf16 pass over
+ * dY (97 MB for timm Mlp.fc1 at the BASELINE shape) disappears. Replaces autograd's bias-gradient reduction of
+ * torch.nn.Linear. */
+int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int64_t M, int64_t N,
+                         int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group, void* workspace,
+                         int64_t workspace_bytes, float* a_colsum, void* stream);
+
 /* y[r,:] = LayerNorm(x'[r,:]) * gamma + beta over the last dim D (<= 2048, multiple of 4); one warp per row.
  * x' = x, or — residual update fused in — x' = x + add_bf16 (a bf16 branch output), with x' also written to
  * x_out (fp32, may be NULL): `x = x + drop_path(attn(...))` / `x = x + mlp(...)` of timm Block.forward and the

@@ -143,6 +143,32 @@ def test_gemm_residual_accumulate_splitk():
     assert torch.equal(o1, o2)                                                 # bit-reproducible
 
 
+@pytest.mark.parametrize("M,N,K,bn,cg,sk,b_mn", [
+    (3072, 768, 15760, 256, 2, 2, True),      # timm Mlp.fc1 weight gradient at the BASELINE shape (dW = dz^T ln2)
+    (768, 768, 15760, 256, 2, 8, True),       # proj: 9 pair tiles, split 8
+    (2304, 768, 4000, 256, 2, 5, True),       # K tail (4000 = 62.5 k-blocks), uneven split
+    (200, 512, 1000, 128, 1, 3, True),        # ragged M (200 rows in 2 tiles), single CTAs, N tile > 1
+    (384, 256, 300, 256, 1, 1, False),        # no split, K-major B
+    (640, 1024, 2048, 256, 2, 4, True),       # ragged pair tile (640 = 2.5 x 256)
+])
+def test_gemm_wgrad_fused_bias_colsum(M, N, K, bn, cg, sk, b_mn):
+    """a_colsum[m] += sum_k A[m, k] while the weight gradient dW = A B^T is computed (A = dY^T, MN-major)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _mk((K, M), g)                                  # dY [rows, out_features]
+    b = _mk((K, N) if b_mn else (N, K), g, 0.05)
+    out = torch.zeros(M, N, device="cuda")
+    col = torch.full((M,), 3.0, device="cuda")          # accumulates onto the existing values
+    ops.gemm(a, b, out, a_mn=True, b_mn=b_mn, split_k=sk, block_n=bn, cta_group=cg, accumulate=sk > 1, a_colsum=col)
+    _check(out, _ref(a, b, True, b_mn), "wgrad with fused colsum")
+    ref = a.double().sum(0) + 3.0
+    assert ((col.double() - ref).norm() / ref.norm()).item() <= 1e-5
+    # and the GEMM result is unchanged w.r.t. the plain path
+    out2 = torch.zeros(M, N, device="cuda")
+    ops.gemm(a, b, out2, a_mn=True, b_mn=b_mn, split_k=1, block_n=bn, cta_group=cg)
+    _check(out2, _ref(a, b, True, b_mn), "plain wgrad")
+
+
 def test_gemm_pos_cls():
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(8)
