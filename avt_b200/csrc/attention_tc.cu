@@ -10,6 +10,7 @@
 // Layout: qkv bf16 [F*N, 3*D], column = s*D + h*64 + d (timm Attention.qkv packing); out bf16 [F*N, D].
 // Replaces timm Attention.forward: q@k^T*scale -> softmax -> attn@v (4 kernels + 80*12*197^2 score tensor).
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -311,10 +312,10 @@ constexpr int kBwBlk = 128 * 128;                 // [128 x 64] bf16 block
 constexpr int kBwSmem = 4 * kBwTile + 4 * kBwBlk + 2 * kTcKeys * 4 + 1024 + 128;
 
 #ifdef AVT_ATTN_TRACE
-#define TRACE_DECL __shared__ unsigned long long trace_t[64]; __shared__ int trace_id[64]; __shared__ int trace_n;
+#define TRACE_DECL __shared__ unsigned long long trace_t[256]; __shared__ int trace_id[256]; __shared__ int trace_n;
 #define TRACE_INIT if (threadIdx.x == 0) trace_n = 0;
-#define TRACE(id) do { if (blockIdx.x == 0) { int i_ = atomicAdd(&trace_n, 1); if (i_ < 64) { trace_t[i_] = global_timer_ns(); trace_id[i_] = (id); } } } while (0)
-#define TRACE_DUMP if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < trace_n && i_ < 64; ++i_) printf("trace %d %llu\n", trace_id[i_], trace_t[i_] - trace_t[0]); }
+#define TRACE(id) do { if (blockIdx.x == 0) { int i_ = atomicAdd(&trace_n, 1); if (i_ < 256) { trace_t[i_] = global_timer_ns(); trace_id[i_] = (id); } } } while (0)
+#define TRACE_DUMP if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < trace_n && i_ < 256; ++i_) printf("trace %d %llu\n", trace_id[i_], trace_t[i_] - trace_t[0]); }
 #else
 #define TRACE_DECL
 #define TRACE_INIT
@@ -581,6 +582,318 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 8) tmem_dealloc(tm, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward, v2
+// Persistent and software-pipelined. The v1 timeline (TRACE, one CTA = one (frame, head)): 4.7 us prologue (tile loads,
+// delta), then per 128-query iteration  threads 1.0-1.3 us -> MMA 1.6-2.9 us -> threads ...  strictly in series
+// (S^T/dP^T single-buffered in TMEM), 2.2 us read-out: 20.6 us per item, 7 rounds of CTAs per layer.
+// v2:
+//   * one CTA per SM walks items (frame, head) = blockIdx.x, +gridDim.x, ...; TMEM / barriers are set up once;
+//   * queries are processed in chunks of 64 columns and S^T / dP^T are double-buffered in TMEM (2 x 128 columns), so the
+//     tensor core computes chunk g+1's scores while the threads turn chunk g into P^T / dS^T, and chunk g's
+//     dV / dK / dQ MMAs run under chunk g+1's thread work;
+//   * P^T ping-pongs between 2 smem blocks, dS^T between 4 (the dQ MMA of a 128-query tile reads two of them);
+//   * delta = rowsum(dO o O) and lse*log2(e) of the NEXT item are prepared by two otherwise idle warps;
+//   * the read-out of dK / dV / dQ overlaps the TMA loads of the next item's tiles.
+// TMEM columns: S^T[b] 128b..+63 | dP^T[b] 128b+64..+127 (b = 0,1) | dV 256 | dK 320 | dQ tile0 384 | dQ tile1 448.
+constexpr int kB2Workers = 8;                      // worker warps (2 per TMEM lane quarter)
+constexpr int kB2Threads = 32 * (kB2Workers + 3);  // + control warp + 2 delta warps
+constexpr int kB2Smem = 4 * kBwTile + 6 * kBwBlk + 4 * kTcKeys * 4 + 256 + 1024;
+
+__global__ void __launch_bounds__(kB2Threads, 1)
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnTcBwdParams p, int items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kBwTile;
+  uint8_t* sQ = sV + kBwTile;
+  uint8_t* sG = sQ + kBwTile;            // dO
+  uint8_t* sP = sG + kBwTile;            // [2][128 keys x 64 queries]  P^T
+  uint8_t* sS = sP + 2 * kBwBlk;         // [4][128 keys x 64 queries]  dS^T
+  float* sNLse = reinterpret_cast<float*>(sS + 4 * kBwBlk);   // [2][208]  -lse * log2(e)   (-inf for q >= N)
+  float* sNDel = sNLse + 2 * kTcKeys;                          // [2][208]  -delta * scale
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sNDel + 2 * kTcKeys);
+  uint64_t* bar_tiles = bars;        // TMA: the item's four tiles landed
+  uint64_t* bar_s = bars + 1;        // [2] S^T/dP^T buffer b computed            (MMA -> workers)
+  uint64_t* bar_p = bars + 3;        // [2] buffer b drained, P^T/dS^T in smem     (256 workers -> control)
+  uint64_t* bar_m2 = bars + 5;       // [2] dV/dK/dQ MMAs of a chunk retired       (MMA -> workers, control)
+  uint64_t* bar_vkfree = bars + 7;   // dV/dK read out of TMEM                     (256 workers -> control)
+  uint64_t* bar_dqfree = bars + 8;   // dQ read out of TMEM                        (256 workers -> control)
+  uint64_t* bar_dfull = bars + 9;    // [2] delta/lse buffer filled                (64 delta threads -> workers)
+  uint64_t* bar_dfree = bars + 11;   // [2] delta/lse buffer no longer needed      (256 workers -> delta warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.N;
+  TRACE_DECL
+  TRACE_INIT
+
+  if (warp == kB2Workers) {
+    if (lane == 0) {
+      TRACE(0);
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      mbar_init(bar_tiles, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bar_s[b], 1);
+        mbar_init(&bar_p[b], 32 * kB2Workers);
+        mbar_init(&bar_m2[b], 1);
+        mbar_init(&bar_dfull[b], 64);
+        mbar_init(&bar_dfree[b], 32 * kB2Workers);
+      }
+      mbar_init(bar_vkfree, 32 * kB2Workers);
+      mbar_init(bar_dqfree, 32 * kB2Workers);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp == kB2Workers) {
+    // ------------------------------------------------------------- control warp: one lane issues TMA + MMA
+    if (lane == 0) {
+      constexpr uint64_t dK_major = smem_desc_sw128(16, 1024);      // K-major operand
+      constexpr uint64_t dMN_1blk = smem_desc_sw128(8192, 1024);    // MN-major, one 64-wide block (N = 64)
+      constexpr uint64_t dMN_2blk = smem_desc_sw128(kBwBlk, 1024);  // MN-major, two 64-wide blocks 16 KB apart (M = 128)
+      constexpr uint32_t idesc_kv = umma_idesc(1, 0, 1, 128, kTcHd);
+      constexpr uint32_t idesc_q = umma_idesc(1, 1, 1, 128, kTcHd);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aG = smem_u32(sG), aP = smem_u32(sP),
+                     aS = smem_u32(sS);
+      auto load_tiles = [&](int item) {
+        const int f = item / p.H, h = item % p.H;
+        mbar_arrive_expect_tx(bar_tiles, 4 * kBwTile);
+        tma_load_2d(&tmQKV, bar_tiles, sQ, h * kTcHd, f * N);
+        tma_load_2d(&tmQKV, bar_tiles, sK, p.D + h * kTcHd, f * N);
+        tma_load_2d(&tmQKV, bar_tiles, sV, 2 * p.D + h * kTcHd, f * N);
+        tma_load_2d(&tmDO, bar_tiles, sG, h * kTcHd, f * N);
+      };
+      // S^T[b] = K_j Q_c^T, dP^T[b] = V_j dO_c^T for chunk index lc = 4 j + c of the current item
+      auto issue_mma1 = [&](int lc, int b) {
+        const int j = lc >> 2, c = lc & 3;
+        const uint32_t idesc1 = umma_idesc(1, 0, 0, 128, c == 3 ? 16 : 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tm + 128 * b, smem_desc_addr(dK_major, aK + j * kBwBlk + k * 32),
+                   smem_desc_addr(dK_major, aQ + c * 8192 + k * 32), idesc1, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tm + 128 * b + 64, smem_desc_addr(dK_major, aV + j * kBwBlk + k * 32),
+                   smem_desc_addr(dK_major, aG + c * 8192 + k * 32), idesc1, k > 0);
+        umma_commit(&bar_s[b]);
+      };
+      uint32_t g = 0;      // chunks processed by this CTA so far (8 per item)
+      uint32_t n = 0;      // items processed by this CTA so far
+      if ((int)blockIdx.x < items) load_tiles(blockIdx.x);
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+        mbar_wait(bar_tiles, n & 1);
+        if (n < 2) TRACE(1);
+        tc_fence_after_sync();
+        issue_mma1(0, g & 1);   // (the buffer was drained: bar_p of chunk g-1 was observed before that chunk's MMA2)
+        for (int lc = 0; lc < 8; ++lc, ++g) {
+          const int j = lc >> 2, c = lc & 3, b = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          if (lc < 7) issue_mma1(lc + 1, b ^ 1);     // next chunk's scores run under this chunk's thread work
+          if (n < 2) TRACE(90 + lc);
+          mbar_wait(&bar_p[b], ph);                   // P^T / dS^T of this chunk are in smem, S^T/dP^T[b] drained
+          if (n < 2) TRACE(100 + lc);
+          if (c == 0) {
+            const uint32_t v = 2 * n + j;             // dV/dK of the previous key tile must have left TMEM
+            if (v > 0) mbar_wait(bar_vkfree, (v - 1) & 1);
+          }
+          if (lc == 1 && n > 0) mbar_wait(bar_dqfree, (n - 1) & 1);   // previous item's dQ was read out
+          tc_fence_after_sync();
+          const int ks = c == 3 ? 1 : 4;              // 16-query k-steps in this chunk
+          const int sb = (((lc >> 1) & 1) << 1) | (c & 1);   // dS^T block: tile parity x chunk parity
+          for (int k = 0; k < ks; ++k) {
+            umma_f16(tm + 256, smem_desc_addr(dK_major, aP + b * kBwBlk + k * 32),
+                     smem_desc_addr(dMN_1blk, aG + c * 8192 + k * 2048), idesc_kv, (c > 0 || k > 0) ? 1u : 0u);
+            umma_f16(tm + 320, smem_desc_addr(dK_major, aS + sb * kBwBlk + k * 32),
+                     smem_desc_addr(dMN_1blk, aQ + c * 8192 + k * 2048), idesc_kv, (c > 0 || k > 0) ? 1u : 0u);
+          }
+          if (c & 1) {   // both halves of query tile t = c/2 are in smem: dQ_t += dS K_j
+            const int t = c >> 1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_f16(tm + 384 + 64 * t, smem_desc_addr(dMN_2blk, aS + (sb & 2) * kBwBlk + k * 2048),
+                       smem_desc_addr(dMN_1blk, aK + j * kBwBlk + k * 2048), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_m2[b]);
+          if (n < 2) TRACE(110 + lc);
+          if (lc == 7) {
+            const int next = item + gridDim.x;
+            if (next < items) {
+              mbar_wait(&bar_m2[b], ph);   // every MMA of this item retired: the four tiles may be overwritten
+              if (n < 2) TRACE(120);
+              load_tiles(next);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp > kB2Workers) {
+    // ------------------------------------------------------------- delta / lse warps (one item ahead)
+    const int t = threadIdx.x - 32 * (kB2Workers + 1);   // 0..63
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+      const int f = item / p.H, h = item % p.H, ip = n & 1;
+      if (n >= 2) mbar_wait(&bar_dfree[ip], ((n >> 1) - 1) & 1);
+      for (int q = t; q < kTcKeys; q += 64) {
+        float d = 0.f, l = -INFINITY;
+        if (q < N) {
+          const uint4* po = reinterpret_cast<const uint4*>(p.out + ((size_t)f * N + q) * p.D + h * kTcHd);
+          const uint4* pg = reinterpret_cast<const uint4*>(p.dout + ((size_t)f * N + q) * p.D + h * kTcHd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 a = __ldg(po + i), b = __ldg(pg + i);
+            d += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
+                 bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+          }
+          l = -p.lse[((size_t)f * p.H + h) * N + q] * 1.4426950408889634f;
+        }
+        sNDel[ip * kTcKeys + q] = -d * p.scale;
+        sNLse[ip * kTcKeys + q] = l;      // -inf for q >= N: exp2(s*c - inf) = 0, the column drops out
+      }
+      mbar_arrive(&bar_dfull[ip]);        // (release semantics: the smem writes above are visible to the waiters)
+    }
+  } else {
+    // ------------------------------------------------------------- 8 worker warps
+    const int quarter = warp & 3, ch = warp >> 2;
+    const int kr = quarter * 32 + lane;                    // key row within the tile == TMEM lane
+    const uint32_t t_lane = tm + (uint32_t(quarter * 32) << 16);
+    const float2 sl2 = f2(p.scale * 1.4426950408889634f);
+    const float2 sc2 = f2(p.scale);
+    uint32_t g = 0, n = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+      const int f = item / p.H, h = item % p.H, ip = n & 1;
+      bf16* dbase = p.dqkv + (size_t)f * N * 3 * p.D + h * kTcHd;
+      const float* nlse = sNLse + ip * kTcKeys;
+      const float* ndel = sNDel + ip * kTcKeys;
+      mbar_wait(&bar_dfull[ip], (n >> 1) & 1);
+      for (int lc = 0; lc < 8; ++lc, ++g) {
+        const int j = lc >> 2, c = lc & 3, b = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        const int key = j * 128 + kr;
+        const bool key_ok = key < N;
+        mbar_wait(&bar_s[b], ph);
+        if (threadIdx.x == 0 && n < 2) TRACE(200 + lc);
+        if (g >= 2) mbar_wait(&bar_m2[b], ((g - 2) >> 1) & 1);   // chunk g-2's MMAs no longer read sP[b] (nor older dS^T blocks)
+        if (threadIdx.x == 0 && n < 2) TRACE(210 + lc);
+        tc_fence_after_sync();
+        const int sb = (((lc >> 1) & 1) << 1) | (c & 1);
+        const int nh = c == 3 ? 1 : 2;                          // 16-column halves of this warp's 32 columns (chunk 3: 16 columns, ch 0 only)
+        if (c < 3 || ch == 0) {
+          for (int hh = 0; hh < nh; ++hh) {
+            const int c0 = ch * 32 + hh * 16;                    // column within the chunk
+            const int q0 = c * 64 + c0;
+            uint32_t sv[16], dv[16];
+            tmem_ld_32x32b_x16(t_lane + 128 * b + c0, sv);
+            tmem_ld_32x32b_x16(t_lane + 128 * b + 64 + c0, dv);
+            float2 ls[8], dl[8];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {   // broadcast smem reads, issued while the TMEM loads are in flight
+              const float4 a4 = *reinterpret_cast<const float4*>(nlse + q0 + 4 * jj);
+              const float4 b4 = *reinterpret_cast<const float4*>(ndel + q0 + 4 * jj);
+              ls[2 * jj] = make_float2(a4.x, a4.y); ls[2 * jj + 1] = make_float2(a4.z, a4.w);
+              dl[2 * jj] = make_float2(b4.x, b4.y); dl[2 * jj + 1] = make_float2(b4.z, b4.w);
+            }
+            tmem_ld_wait();
+            uint32_t pp[8], dd[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float2 a = __ffma2_rn(make_float2(__uint_as_float(sv[2 * jj]), __uint_as_float(sv[2 * jj + 1])), sl2, ls[jj]);
+              const float2 pr = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+              const float2 tt = __ffma2_rn(make_float2(__uint_as_float(dv[2 * jj]), __uint_as_float(dv[2 * jj + 1])), sc2, dl[jj]);
+              const float2 ds = __fmul2_rn(pr, tt);
+              pp[jj] = key_ok ? pack_bf16x2(pr.x, pr.y) : 0u;
+              dd[jj] = key_ok ? pack_bf16x2(ds.x, ds.y) : 0u;
+            }
+            const uint32_t row = kr * 128;
+            const int chunk = c0 >> 3;
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+              const uint32_t o2 = row + (((chunk + q2) ^ (kr & 7)) << 4);
+              *reinterpret_cast<uint4*>(sP + b * kBwBlk + o2) = make_uint4(pp[4 * q2], pp[4 * q2 + 1], pp[4 * q2 + 2], pp[4 * q2 + 3]);
+              *reinterpret_cast<uint4*>(sS + sb * kBwBlk + o2) = make_uint4(dd[4 * q2], dd[4 * q2 + 1], dd[4 * q2 + 2], dd[4 * q2 + 3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(&bar_p[b]);
+        if (threadIdx.x == 0 && n < 2) TRACE(220 + lc);
+        if (c == 3) {
+          // dV_j / dK_j are complete once this chunk's MMAs retire: read them out (32 columns per warp)
+          mbar_wait(&bar_m2[b], ph);
+          if (threadIdx.x == 0 && n < 2) TRACE(230 + lc);
+          tc_fence_after_sync();
+          uint32_t a[32], bb[32];
+          tmem_ld_32x32b_x32(t_lane + 256 + 32 * ch, a);
+          tmem_ld_32x32b_x32(t_lane + 320 + 32 * ch, bb);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          mbar_arrive(bar_vkfree);
+          if (key_ok) {
+            bf16* rk = dbase + (size_t)key * 3 * p.D + p.D + 32 * ch;
+            bf16* rv = rk + p.D;
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) {
+              *reinterpret_cast<uint4*>(rv + 8 * q2) = make_uint4(
+                  pack_bf16x2(__uint_as_float(a[8 * q2]), __uint_as_float(a[8 * q2 + 1])),
+                  pack_bf16x2(__uint_as_float(a[8 * q2 + 2]), __uint_as_float(a[8 * q2 + 3])),
+                  pack_bf16x2(__uint_as_float(a[8 * q2 + 4]), __uint_as_float(a[8 * q2 + 5])),
+                  pack_bf16x2(__uint_as_float(a[8 * q2 + 6]), __uint_as_float(a[8 * q2 + 7])));
+              *reinterpret_cast<uint4*>(rk + 8 * q2) = make_uint4(
+                  pack_bf16x2(__uint_as_float(bb[8 * q2]), __uint_as_float(bb[8 * q2 + 1])),
+                  pack_bf16x2(__uint_as_float(bb[8 * q2 + 2]), __uint_as_float(bb[8 * q2 + 3])),
+                  pack_bf16x2(__uint_as_float(bb[8 * q2 + 4]), __uint_as_float(bb[8 * q2 + 5])),
+                  pack_bf16x2(__uint_as_float(bb[8 * q2 + 6]), __uint_as_float(bb[8 * q2 + 7])));
+            }
+          }
+          if (j == 1) {
+            // dQ: warp (quarter, ch) reads query tile `ch`, rows quarter*32 + lane, all 64 columns (the last MMA2 retired above)
+            const int q = ch * 128 + kr;
+            uint32_t x0[32], x1[32];
+            tmem_ld_32x32b_x32(t_lane + 384 + 64 * ch, x0);
+            tmem_ld_32x32b_x32(t_lane + 384 + 64 * ch + 32, x1);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            mbar_arrive(bar_dqfree);
+            mbar_arrive(&bar_dfree[ip]);
+            if (q < N) {
+              bf16* rq = dbase + (size_t)q * 3 * p.D;
+#pragma unroll
+              for (int q2 = 0; q2 < 4; ++q2) {
+                *reinterpret_cast<uint4*>(rq + 8 * q2) = make_uint4(
+                    pack_bf16x2(__uint_as_float(x0[8 * q2]), __uint_as_float(x0[8 * q2 + 1])),
+                    pack_bf16x2(__uint_as_float(x0[8 * q2 + 2]), __uint_as_float(x0[8 * q2 + 3])),
+                    pack_bf16x2(__uint_as_float(x0[8 * q2 + 4]), __uint_as_float(x0[8 * q2 + 5])),
+                    pack_bf16x2(__uint_as_float(x0[8 * q2 + 6]), __uint_as_float(x0[8 * q2 + 7])));
+                *reinterpret_cast<uint4*>(rq + 32 + 8 * q2) = make_uint4(
+                    pack_bf16x2(__uint_as_float(x1[8 * q2]), __uint_as_float(x1[8 * q2 + 1])),
+                    pack_bf16x2(__uint_as_float(x1[8 * q2 + 2]), __uint_as_float(x1[8 * q2 + 3])),
+                    pack_bf16x2(__uint_as_float(x1[8 * q2 + 4]), __uint_as_float(x1[8 * q2 + 5])),
+                    pack_bf16x2(__uint_as_float(x1[8 * q2 + 6]), __uint_as_float(x1[8 * q2 + 7])));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  TRACE_DUMP
+  if (warp == kB2Workers) tmem_dealloc(tm, 512);
+}
+
 }  // namespace avt
 
 using namespace avt;
@@ -623,6 +936,19 @@ extern "C" int avt_attention_tc_bwd(const void* qkv, const void* out, const void
   AttnTcBwdParams p;
   p.out = reinterpret_cast<const bf16*>(out); p.dout = reinterpret_cast<const bf16*>(dout); p.lse = lse;
   p.dqkv = reinterpret_cast<bf16*>(dqkv); p.N = N; p.H = H; p.D = D; p.scale = scale;
+  static const bool use_v1 = getenv("AVT_ATTN_BWD_V1") != nullptr;   // the one-CTA-per-item kernel, kept for A/B runs
+  if (!use_v1) {
+    static bool configured2 = false;
+    if (!configured2) {
+      AVT_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2Smem));
+      configured2 = true;
+    }
+    const int items = F * H;
+    const int grid = items < num_sms() ? items : num_sms();
+    attn_tc_bwd2_kernel<<<grid, kB2Threads, kB2Smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, p, items);
+    AVT_CUDA_OK(cudaGetLastError());
+    return AVT_OK;
+  }
   attn_tc_bwd_kernel<<<F * H, kTcThreads, kBwSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, p);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;

@@ -34,18 +34,26 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32 * kSumWarps;
 constexpr int kSlotBytes = 2048;  // TMA-store staging slot: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 constexpr int kSmemLimit = 227 * 1024;
 
+constexpr int kMaxStages = 8;
 template <int BN, int CG>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = kEpiWarps * 4 * kSlotBytes + 2 * BN * 4;  // 2 out + 2 in staging slots per warp, bias x2
+  static constexpr int kStagingBytes = kEpiWarps * 4 * kSlotBytes;  // 2 out + 2 in TMA staging slots per epilogue warp
+  static constexpr int kBiasBytes = 2 * BN * 4;
   static constexpr int kBarBytes = 512;
-  static constexpr int kMaxStages = (kSmemLimit - kEpiBytes - kBarBytes) / kStageBytes;
-  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes;
-  static_assert(kStages >= 3, "not enough shared memory for a 3-stage pipeline");
+  // Operand ring depth. Epilogues that leave through plain stores / fp32 atomics (split-K weight gradients) do not need
+  // the 64 KB of TMA staging: that memory becomes two more pipeline stages (256-wide pair tiles: 5 -> 7).
+  static constexpr int stages(bool staging) {
+    const int n = (kSmemLimit - (staging ? kStagingBytes : 0) - kBiasBytes - kBarBytes) / kStageBytes;
+    return n > kMaxStages ? kMaxStages : n;
+  }
+  static constexpr int smem_bytes(bool staging) {
+    return stages(staging) * kStageBytes + (staging ? kStagingBytes : 0) + kBiasBytes + kBarBytes;
+  }
+  static_assert(stages(true) >= 3, "not enough shared memory for a 3-stage pipeline");
 };
 
 struct GemmParams {
@@ -54,6 +62,8 @@ struct GemmParams {
   int tma_out;  // `out` (and bf16 aux_z) leave through TMA stores: 1 = bf16 out, 2 = fp32 out (plain overwrite)
   int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
   int split_slices;  // split-K partials go to out + split*M*ldo (deterministic two-pass) instead of atomics
+  int stages;        // operand ring depth (GemmCfg::stages)
+  int staging;       // TMA staging slots present in shared memory
   int k_rotate;      // producer walks each tile's k-blocks from a tile-dependent start
   float* a_colsum;   // [M] += sum_k A[m, k] (A MN-major only): the bias gradient when A = dY^T of a weight-gradient GEMM
   avt_epilogue_t ep;
@@ -72,16 +82,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using Cfg = GemmCfg<BN, CG>;
   constexpr int BNL = BN / CG;  // B rows (N extent) held by this CTA
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sStageOut = smem + Cfg::kStages * Cfg::kStageBytes;            // [kEpiWarps][2 out + 2 in][kSlotBytes]
-  float* sBias = reinterpret_cast<float*>(sStageOut + kEpiWarps * 4 * kSlotBytes);  // [2][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 2 * BN * 4);
-  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (CG=2: the leader's copy is used)
-  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA          (every CTA's own copy)
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue     (every CTA's own copy)
+  const int nstages = p.stages;
+  uint8_t* sStageOut = smem + nstages * Cfg::kStageBytes;                  // [kEpiWarps][2 out + 2 in][kSlotBytes] (if p.staging)
+  float* sBias = reinterpret_cast<float*>(sStageOut + (p.staging ? Cfg::kStagingBytes : 0));  // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::kBiasBytes);
+  uint64_t* full_bar = bars;                       // [kMaxStages]  TMA -> MMA          (CG=2: the leader's copy is used)
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA          (every CTA's own copy)
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]        MMA -> epilogue     (every CTA's own copy)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA     (CG=2: the leader's copy)
   uint64_t* tin_bar = tempty_bar + 2;              // [kEpiWarps][2] TMA -> epilogue warp (dact_z staging)
   uint64_t* sum_bar = tin_bar + 2 * kEpiWarps;     // [kStages]  MMA -> column-sum warps (stage consumed by the tensor core)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sum_bar + Cfg::kStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sum_bar + kMaxStages);
   const bool do_colsum = A_MN && p.a_colsum != nullptr;
 
   const int warp = threadIdx.x >> 5;
@@ -94,7 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
     if (p.tma_in) tma_prefetch_desc(&tmIn);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], do_colsum ? 1 + kSumWarps : 1);   // a stage is free once the MMA and the column-sum warps left it
       mbar_init(&sum_bar[s], 1);
@@ -163,7 +174,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -211,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           __syncwarp();
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -242,7 +253,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&sum_bar[stage], phase);
             if (mine) {
               const uint8_t* sA = smem + stage * Cfg::kStageBytes + box_off;
-#pragma unroll 4
+#pragma unroll
               for (int r = 0; r < 16; ++r) {
                 const int row = kgrp * 16 + r;
                 const uint4 v = *reinterpret_cast<const uint4*>(sA + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
@@ -252,7 +263,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
           if (mine) {
 #pragma unroll
@@ -631,21 +642,25 @@ struct GemmMaps {
 };
 
 template <int BN, int CG, bool A_MN, bool B_MN>
-static int launch_gemm(const GemmMaps& tm, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   auto kern = gemm_bf16_kernel<BN, CG, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
-    AVT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    const int mx = Cfg::smem_bytes(true) > Cfg::smem_bytes(false) ? Cfg::smem_bytes(true) : Cfg::smem_bytes(false);
+    AVT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     configured = true;
   }
+  GemmParams p = p_in;
+  p.staging = (p.tma_out || p.tma_in) ? 1 : 0;
+  p.stages = Cfg::stages(p.staging != 0);
   const int units = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int groups = num_sms() / CG;
   const int grid = CG * (units < groups ? units : groups);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(p.staging != 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

