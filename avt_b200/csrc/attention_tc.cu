@@ -596,6 +596,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 //   * delta = rowsum(dO o O) and lse*log2(e) of the NEXT item are prepared by two otherwise idle warps;
 //   * the read-out of dK / dV / dQ overlaps the TMA loads of the next item's tiles.
 // TMEM columns: S^T[b] 128b..+63 | dP^T[b] 128b+64..+127 (b = 0,1) | dV 256 | dK 320 | dQ tile0 384 | dQ tile1 448.
+// Measured (TRACE, B200): 113 us/layer vs 144 us for v1. What bounds it now: (1) the small MMAs are operand-fetch
+// bound, not math bound - a K-major SW128 operand serves one 16-element k-step as 32 bytes out of every 128-byte row,
+// so a 128 x 64 x 16 MMA (32 math cycles) spends ~130-190 cycles pulling 128 + 64 smem lines (interleaving independent
+// accumulator chains did not help: 120 us); (2) the worker warps are bound by the TMEM read port (64 B/clk/SM):
+// S^T + dP^T are 64 KB per chunk = ~0.55 us. Next step: 32-byte-slab (SWIZZLE_32B) operand tiles and P^T / dS^T as
+// TMEM A operands, which cut the operand fetch per k-step to a quarter.
 constexpr int kB2Workers = 8;                      // worker warps (2 per TMEM lane quarter)
 constexpr int kB2Threads = 32 * (kB2Workers + 3);  // + control warp + 2 delta warps
 constexpr int kB2Smem = 4 * kBwTile + 6 * kBwBlk + 4 * kTcKeys * 4 + 256 + 1024;

@@ -56,6 +56,7 @@ def _vit_pair(model_type, init):
 @pytest.mark.parametrize("model_type,F,init,dtype", [
     ("vit_test_patch16_32", 3, "stress", torch.float64), ("vit_test_patch16_64", 2, "stress", torch.float64),
     ("vit_test_patch16_64", 5, "default", torch.float64), ("vit_base_patch16_224", 2, "stress", torch.float32),
+    ("vit_large_patch16_224", 1, "stress", torch.float32),       # BASELINE cfg5 backbone: D 1024, 16 heads, 24 layers
 ])
 def test_backbone_forward_backward_vs_oracle(model_type, F, init, dtype):
     ours, ref = _vit_pair(model_type, init)
