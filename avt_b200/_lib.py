@@ -48,6 +48,7 @@ _i64, _i32, _f32, _u64, _vp = C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_voi
 SIGNATURES = {
     "avt_check_device": [],
     "avt_set_sm_limit": [_i32],
+    "avt_set_pdl": [_i32],
     "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp, _i64,
                       _vp],
     "avt_gemm_bf16_colsum": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp,

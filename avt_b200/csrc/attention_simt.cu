@@ -91,6 +91,7 @@ __device__ __forceinline__ void stage_tile(const bf16* __restrict__ g, int64_t l
 
 template <int NP>
 __global__ void __launch_bounds__(kAttWarps * 32) attn_fwd_simt_kernel(const AttnParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int N = p.N, hd = p.hd, pitch = att_pitch(hd);
   bf16* sK = reinterpret_cast<bf16*>(smem_att);
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attn_fwd_simt_kernel(const Att
 // 32 (batch, head) problems of AVT-h spread over ~128 CTAs instead of 32.
 template <int NP>
 __global__ void __launch_bounds__(kAttWarps * 32) attn_bwd_simt_kernel(const AttnParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int N = p.N, hd = p.hd, pitch = att_pitch(hd);
   bf16* sA = reinterpret_cast<bf16*>(smem_att);   // query slices: K     key slices: Q
@@ -292,7 +294,7 @@ static int launch_simt(const AttnParams& p, bool bwd, cudaStream_t st) {
     int gy = 1;
     const int bh = p.B * p.H;
     while (bh * gy < 2 * num_sms() && gy * kAttWarps < p.N) gy *= 2;
-    attn_fwd_simt_kernel<NP><<<dim3(bh, gy), kAttWarps * 32, smem, st>>>(p);
+    launch_kernel(attn_fwd_simt_kernel<NP>, dim3(dim3(bh, gy)), dim3(kAttWarps * 32), smem, st, p);
   } else {
     AVT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_simt_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int bh = p.B * p.H;
@@ -300,7 +302,7 @@ static int launch_simt(const AttnParams& p, bool bwd, cudaStream_t st) {
     const int max_ny = (p.N + kAttWarps - 1) / kAttWarps;
     if (ny > max_ny) ny = max_ny;
     if (ny < 1) ny = 1;
-    attn_bwd_simt_kernel<NP><<<dim3(bh, 2 * ny), kAttWarps * 32, smem, st>>>(p);
+    launch_kernel(attn_bwd_simt_kernel<NP>, dim3(dim3(bh, 2 * ny)), dim3(kAttWarps * 32), smem, st, p);
   }
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;

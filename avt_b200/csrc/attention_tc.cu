@@ -91,6 +91,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // prologue above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 8) {
     // ------------------------------------------------------------- control warp: one lane issues TMA + MMA
@@ -335,6 +337,7 @@ struct AttnTcBwdParams {
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnTcBwdParams p) {
+  pdl_enter();   // this kernel starts its TMA loads in the prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -660,6 +663,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = *tmem_slot;
+  pdl_wait();   // prologue above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp == kB2Workers) {
     // ------------------------------------------------------------- control warp: one lane issues TMA + MMA
@@ -920,7 +925,7 @@ extern "C" int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int 
   AttnTcParams p;
   p.out = reinterpret_cast<bf16*>(out); p.lse = lse; p.N = N; p.H = H; p.D = D; p.F = F; p.scale = scale;
   const int grid = F * H < num_sms() ? F * H : num_sms();
-  attn_tc_fwd_kernel<<<grid, kTcThreads, kTcSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+  launch_kernel(attn_tc_fwd_kernel, dim3(grid), dim3(kTcThreads), kTcSmem, reinterpret_cast<cudaStream_t>(stream), tmQ, tmKV, p);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
@@ -951,11 +956,11 @@ extern "C" int avt_attention_tc_bwd(const void* qkv, const void* out, const void
     }
     const int items = F * H;
     const int grid = items < num_sms() ? items : num_sms();
-    attn_tc_bwd2_kernel<<<grid, kB2Threads, kB2Smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, p, items);
+    launch_kernel(attn_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmDO, p, items);
     AVT_CUDA_OK(cudaGetLastError());
     return AVT_OK;
   }
-  attn_tc_bwd_kernel<<<F * H, kTcThreads, kBwSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, p);
+  launch_kernel(attn_tc_bwd_kernel, dim3(F * H), dim3(kTcThreads), kBwSmem, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmDO, p);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }

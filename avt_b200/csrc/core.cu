@@ -1,4 +1,5 @@
 // Library plumbing: error string, device checks.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -11,6 +12,15 @@ void set_last_error(const char* what, const char* detail, const char* file, int 
 }
 
 static int g_sm_limit = 0;
+static int g_pdl = -1;   // -1: read AVT_PDL from the environment on first use (default on)
+
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("AVT_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
 
 int num_sms_physical();
 int num_sms() {
@@ -34,6 +44,10 @@ int num_sms_physical() {
 extern "C" int avt_abi_version(void) { return 1; }
 extern "C" int avt_set_sm_limit(int n) {
   avt::g_sm_limit = n > 0 ? (n & ~1) : 0;  // even, so CTA pairs still tile the budget
+  return AVT_OK;
+}
+extern "C" int avt_set_pdl(int enable) {
+  avt::g_pdl = enable ? 1 : 0;
   return AVT_OK;
 }
 extern "C" const char* avt_last_error(void) { return avt::g_err; }

@@ -7,6 +7,7 @@ namespace avt {
 
 // ----------------------------------------------------------------------------- fp32 -> bf16 cast
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n8) {
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
@@ -16,6 +17,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
   }
 }
 __global__ void cast_f32_bf16_tail_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t begin, int64_t n) {
+  pdl_enter();
   const int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -26,6 +28,7 @@ __global__ void cast_f32_bf16_tail_kernel(const float* __restrict__ src, bf16* _
 // Conv2d.weight.reshape(D, C*ps*ps). stride == kernel, so this is a pure re-tiling (no im2col blow-up).
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ video, bf16* __restrict__ out, int F, int C, int H, int W, int ps) {
+  pdl_enter();
   const int PW = W / ps, PH = H / ps, P = PW * PH;
   const int K = C * ps * ps, K8 = K / 8;
   const int64_t total = (int64_t)F * (P + 1) * K8;
@@ -53,6 +56,7 @@ patchify_kernel(const float* __restrict__ video, bf16* __restrict__ out, int F, 
 // out[c] += sum_r x[r, c]   (x bf16 [R, ld]); blockDim (32, 8); each thread owns 8 columns.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, int64_t R, int C, int64_t ld, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[8][32 * 8 + 1];
   const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -78,6 +82,7 @@ colsum_bf16_kernel(const bf16* __restrict__ x, int64_t R, int C, int64_t ld, flo
 // s[t, c] = sum_f x[(f*period + t), c]   (x fp32 [F*period, D])
 __global__ void __launch_bounds__(128)
 framesum_kernel(const float* __restrict__ x, int F, int period, int D, float* __restrict__ s) {
+  pdl_enter();
   const int t = blockIdx.y;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= D) return;
@@ -91,6 +96,7 @@ framesum_kernel(const float* __restrict__ x, int F, int period, int D, float* __
 // dpos (+)= s;  dcls (+)= s[0];  dbias (+)= sum_{t>=1} s[t]
 __global__ void pos_cls_apply_kernel(const float* __restrict__ s, int period, int D, float* __restrict__ dpos,
                                      float* __restrict__ dcls, float* __restrict__ dbias, int accumulate) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   float rest = 0.f;
@@ -108,6 +114,7 @@ __global__ void pos_cls_apply_kernel(const float* __restrict__ s, int period, in
 __global__ void __launch_bounds__(256)
 dropout_apply_kernel(const float* __restrict__ x, int64_t n4, float p, uint64_t seed, uint64_t offset,
                      const uint64_t* __restrict__ offset_dev, float* __restrict__ y32, bf16* __restrict__ y16) {
+  pdl_enter();
   const float scale = 1.0f / (1.0f - p);
   if (offset_dev) offset += __ldg(offset_dev);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -130,6 +137,7 @@ dropout_apply_kernel(const float* __restrict__ x, int64_t n4, float p, uint64_t 
 __global__ void __launch_bounds__(256)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, bf16* __restrict__ shadow,
                 int64_t n4, float lr, float mom, float wd, int nesterov, int first) {
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -167,8 +175,8 @@ extern "C" int avt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void
   if (n <= 0) return AVT_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t n8 = n / 8;
-  if (n8 > 0) cast_f32_bf16_kernel<<<grid_for(n8, 256, 8), 256, 0, st>>>(src, reinterpret_cast<bf16*>(dst), n8);
-  if (n8 * 8 < n) cast_f32_bf16_tail_kernel<<<1, 32, 0, st>>>(src, reinterpret_cast<bf16*>(dst), n8 * 8, n);
+  if (n8 > 0) launch_kernel(cast_f32_bf16_kernel, dim3(grid_for(n8, 256, 8)), dim3(256), 0, st, src, reinterpret_cast<bf16*>(dst), n8);
+  if (n8 * 8 < n) launch_kernel(cast_f32_bf16_tail_kernel, dim3(1), dim3(32), 0, st, src, reinterpret_cast<bf16*>(dst), n8 * 8, n);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
@@ -178,7 +186,7 @@ extern "C" int avt_patchify_bf16(const float* video, void* out, int F, int C, in
   AVT_REQUIRE(ps % 8 == 0 && H % ps == 0 && W % ps == 0 && W % 4 == 0, "patch size must be a multiple of 8 dividing H and W");
   AVT_REQUIRE((reinterpret_cast<uintptr_t>(video) & 15) == 0, "video must be 16-byte aligned");
   const int64_t total = (int64_t)F * ((H / ps) * (W / ps) + 1) * (C * ps * ps / 8);
-  patchify_kernel<<<grid_for(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(patchify_kernel, dim3(grid_for(total, 256, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       video, reinterpret_cast<bf16*>(out), F, C, H, W, ps);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
@@ -192,7 +200,7 @@ extern "C" int avt_colsum_bf16(const void* x, int64_t rows, int cols, int64_t ld
   int gy = (num_sms() * 4 + gx - 1) / gx;
   const int64_t max_gy = (rows + 7) / 8;
   if (gy > max_gy) gy = (int)max_gy;
-  colsum_bf16_kernel<<<dim3(gx, gy), dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(colsum_bf16_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const bf16*>(x), rows, cols, ld, out);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
@@ -203,9 +211,9 @@ extern "C" int avt_frame_sum_grads(const float* dx, int F, int period, int D, fl
   AVT_REQUIRE(dx && workspace, "null pointer");
   AVT_REQUIRE(D % 4 == 0, "D must be a multiple of 4");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  framesum_kernel<<<dim3((D / 4 + 127) / 128, period), 128, 0, st>>>(dx, F, period, D, workspace);
+  launch_kernel(framesum_kernel, dim3(dim3((D / 4 + 127) / 128, period)), dim3(128), 0, st, dx, F, period, D, workspace);
   AVT_CUDA_OK(cudaGetLastError());
-  pos_cls_apply_kernel<<<(D + 127) / 128, 128, 0, st>>>(workspace, period, D, dpos, dcls, dbias, accumulate);
+  launch_kernel(pos_cls_apply_kernel, dim3((D + 127) / 128), dim3(128), 0, st, workspace, period, D, dpos, dcls, dbias, accumulate);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
@@ -216,7 +224,7 @@ extern "C" int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t se
   AVT_REQUIRE(n % 4 == 0, "n must be a multiple of 4");
   AVT_REQUIRE(p >= 0.f && p < 1.f, "p must be in [0, 1)");
   if (n <= 0) return AVT_OK;
-  dropout_apply_kernel<<<grid_for(n / 4, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(dropout_apply_kernel, dim3(grid_for(n / 4, 256, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, n / 4, p, seed, offset, offset_dev, y_f32, reinterpret_cast<bf16*>(y_bf16));
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
@@ -227,7 +235,7 @@ extern "C" int avt_sgd_step(float* p, const float* g, float* m, void* p_bf16, in
   AVT_REQUIRE(p && g && m, "null pointer");
   AVT_REQUIRE(n % 4 == 0, "n must be a multiple of 4 (flat buffers are padded)");
   if (n <= 0) return AVT_OK;
-  sgd_step_kernel<<<grid_for(n / 4, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(sgd_step_kernel, dim3(grid_for(n / 4, 256, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       p, g, m, reinterpret_cast<bf16*>(p_bf16), n / 4, lr, momentum, weight_decay, nesterov, first_step);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;

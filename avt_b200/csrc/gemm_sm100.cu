@@ -6,7 +6,8 @@
 //   warp 0      TMA producer  : cp.async.bulk.tensor tiles of A and B into a 128B-swizzled smem ring
 //   warp 1      MMA issuer    : one lane issues tcgen05.mma (K = 16 per instruction); tcgen05.commit releases smem
 //                               slots and publishes the finished accumulator
-//   warps 2..9  epilogue      : tcgen05.ld the accumulator (one row per thread, two warps per TMEM lane quarter),
+//   warps 2..3  column sums of the A operand (bias gradients riding on weight-gradient GEMMs), idle otherwise
+//   warps 4..11 epilogue      : tcgen05.ld the accumulator (one row per thread, two warps per TMEM lane quarter),
 //                               fused epilogue (bias / GELU (+ its derivative) / dropout / residual / pos-embed),
 //                               bf16 results leave through per-warp swizzled smem slots + TMA stores
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -131,10 +132,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-
+  // barriers, TMEM and tensor-map prefetch are set up: only now wait for the previous kernel of the stream (its tail
+  // overlapped all of the above), then let the next kernel start its own prologue
+  pdl_wait();
+  pdl_trigger();
+  // Register re-allocation between the two warpgroup classes: the TMA / MMA / column-sum warps (warpgroup 0) need few
+  // registers, the epilogue warpgroups hold 32-column accumulator chunks and evaluate GELU (+ its derivative) on them -
+  // latency-bound code that only speeds up with more independent chains in flight. 128 x 56 + 256 x 224 = 384 x 168.
+  // (The two setmaxnreg sit in branches that only re-join at the end of the kernel, so each side is compiled for its own budget.)
   const int num_units = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ============================== TMA producer ==============================
     int stage = 0;
@@ -228,15 +238,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 2 + kEpiWarps) {
-    // ============================== column sums of A (warps 10..11; weight-gradient GEMMs with a bias) ==============
+  } else if (warp < 2 + kSumWarps) {
+    // ============================== column sums of A (warps 2..3; weight-gradient GEMMs with a bias) ==============
     // A = dY^T arrives MN-major: per stage two [64 k][64 m] boxes, 128-byte rows, SWIZZLE_128B. The MMA's commit on
     // sum_bar says the tensor core is done with the stage (so the bytes are there); these warps add the 64 k-rows of
     // every m column of the n-tile-0 units into registers, then release the stage. The reduction over the 15 760
     // activation rows rides on operand bytes that are in shared memory anyway: no separate pass over dY in HBM.
     if constexpr (A_MN) {
       if (do_colsum) {
-        const int t = threadIdx.x - 32 * (2 + kEpiWarps);     // 0..63
+        const int t = threadIdx.x - 64;                        // 0..63
         const int chunk = t & 15;                              // 8 m values (16 bytes): box = chunk / 8
         const int kgrp = t >> 4;                               // 16 k rows each
         const uint32_t box_off = (chunk >> 3) * 8192;
@@ -277,14 +287,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+  }
   } else {
-    // ============================== epilogue (warps 2..9) ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ============================== epilogue (warps 4..11) ==============================
     // Math runs on packed fp32x2 (FFMA2): the fused epilogues are issue-bound, two columns per instruction.
     const avt_epilogue_t& ep = p.ep;
-    const int ew = warp - 2;
+    const int ew = warp - (2 + kSumWarps);
     const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the only ones this warp may read
     const int chalf = ew >> 2;      // which half of the tile's columns this warp handles
-    const int etid = threadIdx.x - 64;
+    const int etid = threadIdx.x - 32 * (2 + kSumWarps);
     uint8_t* out_slots = sStageOut + ew * 4 * kSlotBytes;   // [2] staging for TMA stores
     uint8_t* in_slots = out_slots + 2 * kSlotBytes;         // [2] staging for TMA loads (dact_z)
     uint64_t* in_bar = tin_bar + ew * 2;
@@ -415,15 +427,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (ep.aux_z) {
-          float2 a[16];
-          if (ep.aux_mode == 1) act_chunk<2>(ep.act, v, a);  // save act'(pre-activation): backward only multiplies
-          else act_chunk<1>(ep.act, v, a);
           if (p.tma_out == 1) {
-            tma_store_chunk(&tmAux, a, col0, row0);
-          } else if (row_ok) {
-            uint4* zp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col0);
+            // act (and act') computed, packed and staged 16 bytes at a time; the saved tensor never sits in registers
+            uint8_t* slot = out_slots + (n_st & 1) * kSlotBytes;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            if (ep.aux_mode == 1) act_chunk_to_slot<2>(ep.act, v, slot + lane * 64, sw);  // save act'(pre-activation)
+            else act_chunk_to_slot<1>(ep.act, v, slot + lane * 64, sw);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmAux, slot, col0, row0);
+              tma_store_commit();
+            }
+            ++n_st;
+          } else {
+            float2 a[16];
+            if (ep.aux_mode == 1) act_chunk<2>(ep.act, v, a);  // save act'(pre-activation): backward only multiplies
+            else act_chunk<1>(ep.act, v, a);
+            if (row_ok) {
+              uint4* zp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 4 * j);
+              for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 4 * j);
+            }
           }
         } else if (ep.act != AVT_ACT_NONE) {
           float2 unused[16];
@@ -524,6 +550,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // epilogue as the fused path. Only used for the weight-streaming M <= 128 GEMMs of AVT-h (80 x N elements).
 __global__ void __launch_bounds__(256)
 epilogue_apply_kernel(const float* __restrict__ acc, int nslices, int M, int N, const avt_epilogue_t ep) {
+  pdl_enter();
   const int64_t total4 = (int64_t)M * N / 4;
   const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
   const uint64_t drop_off = ep.drop_offset + ((ep.drop_p > 0.f && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
@@ -786,7 +813,7 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     const int64_t total4 = M * N / 4;
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-    epilogue_apply_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(workspace), p.split_k, (int)M, (int)N, finish);
+    launch_kernel(epilogue_apply_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const float*>(workspace), p.split_k, (int)M, (int)N, finish);
     AVT_CUDA_OK(cudaGetLastError());
   }
   return AVT_OK;

@@ -18,6 +18,7 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const bf16* __restr
               float* __restrict__ x_out, int64_t xo_stride, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, int64_t rows, int D, void* __restrict__ y, int y_fp32,
               int64_t y_stride, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * kLnWarps;
@@ -78,6 +79,7 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, const
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               int64_t rows, int D, const float* __restrict__ dx_in, float* __restrict__ dx_out, int64_t dx_stride,
               bf16* __restrict__ dx_bf16, int64_t dxb_stride, float* __restrict__ partial /*[grid][2][D]*/) {
+  pdl_enter();
   __shared__ float red[kLnWarps][32 * 4 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_global = (int64_t)blockIdx.x * kLnWarps + warp;
@@ -178,6 +180,7 @@ ln_bwd_pipe_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, 
                    const float* __restrict__ gamma, int64_t rows, int D, const float* dx_in, float* dx_out,
                    int64_t dx_stride, bf16* __restrict__ dx_bf16, int64_t dxb_stride, int ncols_out /*2 or 3*/,
                    float* __restrict__ partial /*[grid][ncols_out][D]*/) {
+  pdl_enter();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t x_bytes = (uint32_t)D * 4u, dy_bytes = (uint32_t)D * (dy_fp32 ? 4u : 2u);
@@ -324,6 +327,7 @@ ln_fwd_row_kernel(const float* __restrict__ x, int64_t x_stride, const bf16* __r
                   float* __restrict__ x_out, int64_t xo_stride, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, int D, void* __restrict__ y, int y_fp32, int64_t y_stride,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_enter();
   __shared__ float red[kLnRowThreads / 32][2];
   const int64_t r = blockIdx.x;
   const float inv_d = 1.0f / (float)D;
@@ -382,6 +386,7 @@ ln_bwd_row_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, c
                   int64_t x_stride, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ gamma, int D, const float* dx_in, float* dx_out, int64_t dx_stride,
                   bf16* __restrict__ dx_bf16, int64_t dxb_stride, int ncols_out, float* __restrict__ partial /*[rows][ncols_out][D]*/) {
+  pdl_enter();
   __shared__ float red[kLnRowThreads / 32][2];
   const int64_t r = blockIdx.x;
   const float mu = mean[r], rs = rstd[r];
@@ -433,6 +438,7 @@ ln_bwd_row_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, c
 __global__ void __launch_bounds__(256)
 ln_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int D, int ncols_out, float* __restrict__ dgamma,
                           float* __restrict__ dbeta, float* __restrict__ dcol, int accumulate) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int total = ncols_out * D;
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -461,6 +467,7 @@ ln_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int D, 
 // out[c] (+)= sum_r x[r, c] for fp32 x (only behind the register-resident fallback kernel)
 __global__ void __launch_bounds__(256)
 colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int D, int64_t ld, float* __restrict__ out, int accumulate) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -483,7 +490,7 @@ static int launch_fwd(const float* x, int64_t xs, const bf16* add, int64_t as, f
   int64_t blocks = (rows + kLnWarps - 1) / kLnWarps;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  ln_fwd_kernel<VPT><<<(int)blocks, kLnWarps * 32, 0, st>>>(x, xs, add, as, xo, xos, g, b, eps, rows, D, y, y_fp32, ys, mean, rstd);
+  launch_kernel(ln_fwd_kernel<VPT>, dim3((int)blocks), dim3(kLnWarps * 32), 0, st, x, xs, add, as, xo, xos, g, b, eps, rows, D, y, y_fp32, ys, mean, rstd);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
@@ -516,7 +523,7 @@ static int launch_bwd_pipe(const void* dy, int dy_fp32, int64_t dys, const float
     AVT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<blocks, kLnPipeWarps * 32, smem, st>>>(dy, dy_fp32, dys, x, xs, mean, rstd, gamma, rows, D, dx_in, dx_out, dxs, dxb,
+  launch_kernel(kern, dim3(blocks), dim3(kLnPipeWarps * 32), smem, st, dy, dy_fp32, dys, x, xs, mean, rstd, gamma, rows, D, dx_in, dx_out, dxs, dxb,
                                                 dxbs, ncols_out, partial);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
@@ -548,10 +555,10 @@ extern "C" int avt_layernorm_fwd(const float* x, int64_t x_stride, const void* a
   const bf16* add = reinterpret_cast<const bf16*>(add_bf16);
   if (rows <= ln_row_kernel_max_rows()) {
     if (D <= 1024)
-      ln_fwd_row_kernel<1><<<(int)rows, kLnRowThreads, 0, st>>>(x, x_stride, add, add_stride, x_out, x_out_stride, gamma, beta,
+      launch_kernel(ln_fwd_row_kernel<1>, dim3((int)rows), dim3(kLnRowThreads), 0, st, x, x_stride, add, add_stride, x_out, x_out_stride, gamma, beta,
                                                                 eps, D, y, y_fp32, y_stride, mean, rstd);
     else
-      ln_fwd_row_kernel<2><<<(int)rows, kLnRowThreads, 0, st>>>(x, x_stride, add, add_stride, x_out, x_out_stride, gamma, beta,
+      launch_kernel(ln_fwd_row_kernel<2>, dim3((int)rows), dim3(kLnRowThreads), 0, st, x, x_stride, add, add_stride, x_out, x_out_stride, gamma, beta,
                                                                 eps, D, y, y_fp32, y_stride, mean, rstd);
     AVT_CUDA_OK(cudaGetLastError());
     return AVT_OK;
@@ -589,10 +596,10 @@ extern "C" int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride,
   if (rows <= ln_row_kernel_max_rows()) {
     nparts = (int)rows;
     if (D <= 1024)
-      ln_bwd_row_kernel<1><<<nparts, kLnRowThreads, 0, st>>>(dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, D, dx_in,
+      launch_kernel(ln_bwd_row_kernel<1>, dim3(nparts), dim3(kLnRowThreads), 0, st, dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, D, dx_in,
                                                              dx_out, dx_stride, dxb, dxb_stride, ncols_out, partial);
     else
-      ln_bwd_row_kernel<2><<<nparts, kLnRowThreads, 0, st>>>(dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, D, dx_in,
+      launch_kernel(ln_bwd_row_kernel<2>, dim3(nparts), dim3(kLnRowThreads), 0, st, dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, D, dx_in,
                                                              dx_out, dx_stride, dxb, dxb_stride, ncols_out, partial);
     AVT_CUDA_OK(cudaGetLastError());
   } else if (pipe_ok) {
@@ -605,16 +612,16 @@ extern "C" int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride,
   } else {
     nparts = ln_bwd_blocks(rows);
     ncols_out = 2;
-    AVT_LN_DISPATCH(D, (ln_bwd_kernel<V><<<nparts, kLnWarps * 32, 0, st>>>(
+    AVT_LN_DISPATCH(D, (launch_kernel(ln_bwd_kernel<V>, dim3(nparts), dim3(kLnWarps * 32), 0, st, 
                            dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, rows, D, dx_in, dx_out, dx_stride, dxb,
                            dxb_stride, partial)));
     AVT_CUDA_OK(cudaGetLastError());
     if (dx_colsum) {
-      colsum_f32_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(dx_out, rows, D, dx_stride, dx_colsum, accumulate);
+      launch_kernel(colsum_f32_kernel, dim3((D + 31) / 32), dim3(dim3(32, 8)), 0, st, dx_out, rows, D, dx_stride, dx_colsum, accumulate);
       AVT_CUDA_OK(cudaGetLastError());
     }
   }
-  ln_reduce_partials_kernel<<<(ncols_out * D + 31) / 32, dim3(32, 8), 0, st>>>(partial, nparts, D, ncols_out, dgamma, dbeta,
+  launch_kernel(ln_reduce_partials_kernel, dim3((ncols_out * D + 31) / 32), dim3(dim3(32, 8)), 0, st, partial, nparts, D, ncols_out, dgamma, dbeta,
                                                                               dx_colsum, accumulate);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;

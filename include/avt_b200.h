@@ -37,6 +37,11 @@ int avt_check_device(void);
 /* Cap the number of SMs the persistent kernels (GEMM) occupy; 0 = all. Used while an NCCL all-reduce runs
  * concurrently: a persistent grid that assumes every SM is free is stretched 2x by the SMs the collective holds. */
 int avt_set_sm_limit(int n);
+/* Programmatic dependent launch (default on; environment AVT_PDL=0 or avt_set_pdl(0) turns it off). Every kernel of
+ * the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and executes griddepcontrol.wait
+ * before it touches global memory, so the ~550 dependent launches of a training step overlap their launch latency and
+ * prologue (barrier init, TMEM allocation, tensor-map prefetch) with the tail of the previous kernel. */
+int avt_set_pdl(int enable);
 
 /* Fused-epilogue description for avt_gemm_bf16. All pointers may be NULL (feature off).
  * Per output element (r, c), in this order:
