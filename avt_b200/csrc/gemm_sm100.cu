@@ -325,19 +325,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ++n_st;
     };
     auto tma_store_chunk_f32 = [&](const CUtensorMap* tm, const float2* v, int col0, int row0) {
-      // 32 rows x 32 fp32 = 4 KB: both out slots as one buffer, 128-byte rows, SWIZZLE_128B (chunk ^= row & 7)
-      if (lane == 0) tma_store_wait_read<0>();
+      // 32 rows x 32 fp32 = 4 KB, 128-byte rows, SWIZZLE_128B (chunk ^= row & 7). Two buffers when the dact_z staging
+      // slots are free (both out slots / both in slots): the next chunk is staged while the TMA drains this one - the
+      // weight gradients of AVT-h (contraction over 80 rows) are nothing but this epilogue streaming 67 MB to HBM.
+      uint8_t* buf = out_slots + ((!p.tma_in && (n_st & 1)) ? 2 * kSlotBytes : 0);
+      if (lane == 0) {
+        if (p.tma_in) tma_store_wait_read<0>();
+        else tma_store_wait_read<1>();
+      }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(out_slots + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
             make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tm, out_slots, col0, row0);
+        tma_store_2d(tm, buf, col0, row0);
         tma_store_commit();
       }
+      ++n_st;
     };
     auto issue_in = [&](int col0, int row0) {   // prefetch a 32 x 32 bf16 block of dact_z into a staging slot
       if (lane == 0) {

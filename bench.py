@@ -281,8 +281,14 @@ def run_ours(args):
                                     "sample": f"oracle port of the reference path (fp32, train mode), 1 clip x {T} frames, mean of 2 steps after 1 warm-up"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # A live CUDA graph that captured NCCL kernels can block ncclCommDestroy forever (seen on 2 x B200: the JSON
+        # line was out, the workers never exited). Nothing is left to save: leave without the collective tear-down.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(30.0 if rank == 0 else 150.0, lambda: os._exit(0)).start()   # never outlive the result
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
