@@ -63,6 +63,7 @@ struct GemmParams {
   int tma_out;  // `out` (and bf16 aux_z) leave through TMA stores: 1 = bf16 out, 2 = fp32 out (plain overwrite)
   int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
   int split_slices;  // split-K partials go to out + split*M*ldo (deterministic two-pass) instead of atomics
+  int stream_k;      // atomics path only: the tiles' k-blocks are dealt out as ONE contiguous range per CTA group
   int stages;        // operand ring depth (GemmCfg::stages)
   int staging;       // TMA staging slots present in shared memory
   int k_rotate;      // producer walks each tile's k-blocks from a tile-dependent start
@@ -74,6 +75,49 @@ __device__ __forceinline__ uint4 pack8(const float2* v) {  // 4 float2 = 8 conse
   return make_uint4(pack_bf16x2(v[0].x, v[0].y), pack_bf16x2(v[1].x, v[1].y), pack_bf16x2(v[2].x, v[2].y),
                     pack_bf16x2(v[3].x, v[3].y));
 }
+
+// One unit of work of a CTA group: k-blocks [kb0, kb1) of output tile `tile`; `split` = slice index of uniform split-K.
+struct Work {
+  int tile, kb0, kb1, split;
+  bool shared;   // other groups contribute to the same tile: partial sums meet in fp32 atomics / workspace slices
+};
+// Every warp role walks the same sequence. Uniform mode: units (tile, split) round-robin over the groups. Stream-K mode
+// (weight gradients: few tiles, very long K, fp32 atomics into the output): the tiles x k-blocks space is cut into one
+// contiguous range per group, so every group does the same number of k-blocks whatever the tile count and however many
+// SMs the grid was given (72 units on 74 CTA pairs waste 3 %; on the 70 pairs left beside an NCCL all-reduce they would
+// need two rounds).
+struct WorkIter {
+  int ngroups, unit, pos, end;
+  __device__ WorkIter(const GemmParams& p, int group, int ngroups_) : ngroups(ngroups_), unit(group), pos(0), end(0) {
+    if (p.stream_k) {
+      const int total = p.num_m_tiles * p.num_n_tiles * p.num_k_blocks;
+      const int q = (total + ngroups - 1) / ngroups;
+      pos = min(group * q, total);
+      end = min(pos + q, total);
+    }
+  }
+  __device__ __forceinline__ bool next(const GemmParams& p, Work& w) {
+    if (p.stream_k) {
+      if (pos >= end) return false;
+      const int nkb = p.num_k_blocks;
+      w.tile = pos / nkb;
+      w.kb0 = pos - w.tile * nkb;
+      w.kb1 = min(nkb, w.kb0 + (end - pos));
+      w.split = 0;
+      w.shared = true;
+      pos += w.kb1 - w.kb0;
+      return true;
+    }
+    if (unit >= p.num_m_tiles * p.num_n_tiles * p.split_k) return false;
+    w.tile = unit / p.split_k;
+    w.split = unit % p.split_k;
+    w.kb0 = w.split * p.kb_per_split;
+    w.kb1 = min(w.kb0 + p.kb_per_split, p.num_k_blocks);
+    w.shared = p.split_k > 1;
+    unit += ngroups;
+    return true;
+  }
+};
 
 template <int BN, int CG, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -140,8 +184,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // registers, the epilogue warpgroups hold 32-column accumulator chunks and evaluate GELU (+ its derivative) on them -
   // latency-bound code that only speeds up with more independent chains in flight. 128 x 56 + 256 x 224 = 384 x 168.
   // (The two setmaxnreg sit in branches that only re-join at the end of the kernel, so each side is compiled for its own budget.)
-  const int num_units = p.num_m_tiles * p.num_n_tiles * p.split_k;
-  const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
+  const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
+  Work wk;
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -149,12 +193,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ============================== TMA producer ==============================
     int stage = 0;
     uint32_t phase = 0;
-    for (int unit = unit0; unit < num_units; unit += unit_stride) {
-      const int tile = unit / p.split_k, split = unit % p.split_k;
+    for (WorkIter it(p, group, ngroups); it.next(p, wk);) {
+      const int tile = wk.tile;
       const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * BNL;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+      const int kb0 = wk.kb0, kb1 = wk.kb1;
       // weight-streaming GEMMs (M <= 128): every CTA reads the SAME A k-blocks; starting each tile at a different
       // k offset keeps 100+ SMs from queueing on one L2 slice at the same moment (the sum order is irrelevant)
       const int nkb = kb1 - kb0;
@@ -201,10 +244,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int split = unit % p.split_k;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+      for (WorkIter it(p, group, ngroups); it.next(p, wk);) {
+        const int kb0 = wk.kb0, kb1 = wk.kb1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // every epilogue warp has drained this accumulator
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -252,12 +293,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t box_off = (chunk >> 3) * 8192;
         int stage = 0;
         uint32_t phase = 0;
-        for (int unit = unit0; unit < num_units; unit += unit_stride) {
-          const int tile = unit / p.split_k, split = unit % p.split_k;
+        for (WorkIter it(p, group, ngroups); it.next(p, wk);) {
+          const int tile = wk.tile;
           const bool mine = (tile % p.num_n_tiles) == 0;
           const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
-          const int kb0 = split * p.kb_per_split;
-          const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+          const int kb0 = wk.kb0, kb1 = wk.kb1;
           float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&sum_bar[stage], phase);
@@ -356,9 +396,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ++n_in_issued;
     };
 
-    for (int unit = unit0; unit < num_units; unit += unit_stride) {
-      const int tile = unit / p.split_k;
-      const int split = unit % p.split_k;
+    for (WorkIter it(p, group, ngroups); it.next(p, wk);) {
+      const int tile = wk.tile;
+      const int split = wk.split;
       const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
       const int row0 = m0 + quarter * 32;
@@ -509,7 +549,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
-            } else if (p.split_k > 1) {
+            } else if (wk.shared) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 atomicAdd(reinterpret_cast<float4*>(op + 4 * j), make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y));
@@ -688,7 +728,7 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t 
   GemmParams p = p_in;
   p.staging = (p.tma_out || p.tma_in) ? 1 : 0;
   p.stages = Cfg::stages(p.staging != 0);
-  const int units = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int units = p.num_m_tiles * p.num_n_tiles * (p.stream_k ? p.num_k_blocks : p.split_k);
   const int groups = num_sms() / CG;
   const int grid = CG * (units < groups ? units : groups);
   cudaLaunchConfig_t cfg{};
@@ -774,6 +814,7 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     AVT_CUDA_OK(cudaMemset2DAsync(p.ep.out, (size_t)p.ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s));
   }
   p.split_slices = 0;
+  p.stream_k = (!two_pass && p.split_k > 1) ? 1 : 0;   // fp32 atomics: balance the k-blocks over whatever grid there is
   if (two_pass && p.split_k > 1) {
     p.split_slices = 1;
     p.ep = avt_epilogue_t{};
