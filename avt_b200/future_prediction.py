@@ -138,7 +138,18 @@ class AVTh(nn.Module):
         self._pack = None
         self._stack = None
         self._rng_dev = None
+        # Checkpoints written with the reference's transformers==4.2.2 carry the causal-mask buffers of every
+        # GPT2Attention (`h.{i}.attn.bias` [1,1,n_ctx,n_ctx], `h.{i}.attn.masked_bias`); the mask is implicit in the
+        # kernels here, so those keys are dropped before a (strict) load instead of failing the resume of
+        # func/train.py:764 / the released checkpoint.pth files (README.md:193).
+        self._register_load_state_dict_pre_hook(self._drop_hf_mask_buffers)
         self._aux = {}
+
+    @staticmethod
+    def _drop_hf_mask_buffers(state_dict, prefix, *unused):
+        for k in [k for k in state_dict if k.startswith(prefix + "gpt_model.h.") and
+                  (k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"))]:
+            del state_dict[k]
 
     # ------------------------------------------------------------------ plumbing
     def _ensure_pack(self, device):

@@ -228,9 +228,11 @@ def run_ours(args):
     e2e_value = world * B / (ms_e2e * 1e-3)
     h2d = video_h.numel() * 4 + target_h.numel() * 8 + sub_h.numel() * 8
 
-    # dominant kernel (the tcgen05 GEMM): one instrumented step, every GEMM launch bracketed by CUDA events
+    # dominant kernel (the tcgen05 GEMM): one instrumented step, every GEMM launch bracketed by CUDA events. The big
+    # ViT GEMMs (M = frames x tokens rows) are tensor-bound; the AVT-h GEMMs (M = clips x frames = 80 rows) stream
+    # 604 MB of weights per pass and are HBM-bound: they are reported against their own roofline.
     sus, burst, hbm, src = peaks()
-    gemm_flops, gemm_events = [], []
+    vit_flops, vit_events, head_bytes, head_events = [], [], [], []
     orig = ops.gemm
 
     def timed_gemm(a, b, out, **kw):
@@ -239,16 +241,23 @@ def run_ours(args):
         r = orig(a, b, out, **kw)
         e1.record()
         K = a.shape[0] if kw.get("a_mn") else a.shape[1]
-        gemm_flops.append(2.0 * out.shape[0] * out.shape[1] * K)
-        gemm_events.append((e0, e1))
+        M_, N_ = out.shape
+        if min(M_, N_, K) > 128:
+            vit_flops.append(2.0 * M_ * N_ * K)
+            vit_events.append((e0, e1))
+        else:   # algorithmic bytes: every operand and the output once
+            head_bytes.append(a.numel() * a.element_size() + b.numel() * b.element_size() + out.numel() * out.element_size())
+            head_events.append((e0, e1))
         return r
 
     ops.gemm = timed_gemm
     core(video_d, target_d, past_targets(sub_d))                     # eager, so that the events bracket each launch
     torch.cuda.synchronize()
     ops.gemm = orig
-    gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
-    gemm_tf = sum(gemm_flops) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    gemm_ms = sum(a.elapsed_time(b) for a, b in vit_events)
+    gemm_tf = sum(vit_flops) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    head_ms = sum(a.elapsed_time(b) for a, b in head_events)
+    head_gbs = sum(head_bytes) / (head_ms * 1e-3) / 1e9 if head_ms > 0 else 0.0
     gflop_clip = GFLOP_PER_CLIP.get((args.model, T))
     step_tf = (gflop_clip * 1e9 * B / (ms_per_step * 1e-3) / 1e12) if gflop_clip else None
 
@@ -268,10 +277,19 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus,
-                         "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05)", "peak_source": f"{src} bf16_tflops_sustained",
-                         "how": "sum of 2*M*N*K over every GEMM launch of one step / sum of their CUDA-event durations",
-                         "launches": len(gemm_events), "gemm_ms_per_step": gemm_ms, "step_achieved": step_tf,
+                         "traffic": 98.5e6, "kernel": "gemm_bf16_kernel (tcgen05), ViT GEMMs (M = 15 760 rows)",
+                         "peak_source": f"{src} bf16_tflops_sustained",
+                         "how": "sum of 2*M*N*K over the ViT GEMM launches of one step / sum of their CUDA-event durations",
+                         "traffic_source": "profiles/r01_step_launches.md: ncu dram__bytes_read+write, mean per launch of the "
+                                           "172 ViT GEMM launches of one step (algorithmic operand+output bytes: 97 MB)",
+                         "launches": len(vit_events), "gemm_ms_per_step": gemm_ms, "step_achieved": step_tf,
                          "step_frac": (step_tf / sus) if step_tf else None},
+            "roofline_head": {"bound": "hbm", "achieved": head_gbs, "peak": hbm, "unit": "GB/s",
+                              "frac": head_gbs / hbm, "traffic": None,
+                              "kernel": "gemm_bf16_kernel (tcgen05), weight-streaming AVT-h GEMMs (M = 80 rows)",
+                              "launches": len(head_events), "gemm_ms_per_step": head_ms,
+                              "how": "operand + output bytes of every AVT-h GEMM launch / sum of their CUDA-event durations "
+                                     "(eager launches: includes ~10 us of launch/ramp per call)"},
         }
         if args.cpu_baseline:
             cores = torch.get_num_threads()

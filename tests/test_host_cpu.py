@@ -76,6 +76,31 @@ def test_avth_interface_matches_reference_names_and_errors():
             fp.AVTh(**bad)
 
 
+def test_checkpoint_key_compatibility():
+    """timm ImageNet checkpoints (extra `head.*`) load into backbone.model with strict=False exactly as
+    func/train.py:679-688 does, and head checkpoints written under transformers 4.2.2 (per-layer causal-mask buffers
+    `attn.bias` / `attn.masked_bias`) load STRICTLY, also through a parent module's prefix."""
+    import torch
+    from avt_b200.backbone import TIMMModel
+    from avt_b200.future_prediction import AVTh
+    bb = TIMMModel(1, "vit_test_patch16_32")
+    sd = {k: torch.randn_like(v) for k, v in bb.model.state_dict().items()}
+    sd["head.weight"], sd["head.bias"] = torch.zeros(10, sd["norm.weight"].numel()), torch.zeros(10)
+    res = bb.model.load_state_dict(sd, strict=False)
+    assert res.missing_keys == [] and sorted(res.unexpected_keys) == ["head.bias", "head.weight"]
+    assert torch.equal(bb.model.state_dict()["blocks.0.attn.qkv.weight"], sd["blocks.0.attn.qkv.weight"])
+    head = AVTh(64, n_head=2, n_layer=2, inter_dim=64, n_positions=32)
+    hsd = {k: torch.randn_like(v) for k, v in head.state_dict().items()}
+    for i in range(2):
+        hsd[f"gpt_model.h.{i}.attn.bias"] = torch.ones(1, 1, 32, 32)
+        hsd[f"gpt_model.h.{i}.attn.masked_bias"] = torch.tensor(-1e4)
+    head.load_state_dict(dict(hsd), strict=True)
+    assert torch.equal(head.state_dict()["gpt_model.h.1.attn.c_attn.weight"], hsd["gpt_model.h.1.attn.c_attn.weight"])
+    parent = torch.nn.Module()
+    parent.future_predictor = AVTh(64, n_head=2, n_layer=2, inter_dim=64, n_positions=32)
+    parent.load_state_dict({"future_predictor." + k: v for k, v in hsd.items()}, strict=True)
+
+
 def test_split_k_heuristic():
     """Wave-aware split-K: units = tiles x split must not spill a few units into an extra round of the persistent grid."""
     from avt_b200.engine import _best_split, _split_k_for, small_m_split
