@@ -29,19 +29,25 @@ namespace avt {
 constexpr int kBM = 128;        // accumulator rows per CTA (UMMA M = 128 per CTA, 256 per pair)
 constexpr int kBK = 64;         // K per smem stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
-constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int kSumWarps = 2;     // column sums of the A operand (bias gradients fused into the weight-gradient GEMM)
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32 * kSumWarps;
+// Epilogue warps: two per TMEM lane quarter, each takes half of the tile's columns. The kernel is written for 8 or 12
+// (three per quarter, 3 / 3 / 2 of the eight 32-column chunks), but 12 bought nothing on B200: the fused erf-GELU epilogue
+// is bound by the per-scheduler pipes (64 MUFU x 8 cycles + 240 packed FMA x 2 cycles + ~100 ALU x 2 per chunk, issued
+// back to back: ~12 k cycles per 128 x 256 tile against a 9.4 k-cycle main loop), not by per-warp latency, and every
+// scheduler sees the same eight chunks per tile whichever way they are dealt (78.1 us vs 78.5 us, tools/sweep.py fc1).
+__host__ __device__ constexpr int epi_warps(int epi) { return epi >= 0 ? 8 : 12; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * kSumWarps + 32 * epi_warps(epi); }
 constexpr int kSlotBytes = 2048;  // TMA-store staging slot: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 constexpr int kSmemLimit = 227 * 1024;
 
 constexpr int kMaxStages = 8;
-template <int BN, int CG>
+static int g_epi_special = 1;   // avt_set_gemm_specialized_epilogues(0): always run the generic epilogue (A/B, tests)
+template <int BN, int CG, int EW = 8>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 4 * kSlotBytes;  // 2 out + 2 in TMA staging slots per epilogue warp
+  static constexpr int kStagingBytes = EW * 4 * kSlotBytes;  // 2 out + 2 in TMA staging slots per epilogue warp
   static constexpr int kBiasBytes = 2 * BN * 4;
   static constexpr int kBarBytes = 512;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator
@@ -119,12 +125,19 @@ struct WorkIter {
   }
 };
 
-template <int BN, int CG, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// Epilogue classes (template parameter EPI)
+constexpr int kEpiGeneric = 0;   // everything avt_epilogue_t can express, decided at run time
+constexpr int kEpiStore = 1;     // [+ bias] -> bf16, TMA store                              (qkv / proj / fc2, plain dgrads)
+constexpr int kEpiGeluAux = 2;   // [+ bias], erf-GELU and its derivative -> two bf16 TMA stores (timm Mlp.fc1 forward)
+constexpr int kEpiMulZ = 3;      // x saved gelu' (TMA-loaded) -> bf16, TMA store               (fc2 dgrad through the GELU)
+
+template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  constexpr int kEpiWarps = epi_warps(EPI);
+  using Cfg = GemmCfg<BN, CG, kEpiWarps>;
   constexpr int BNL = BN / CG;  // B rows (N extent) held by this CTA
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nstages = p.stages;
@@ -188,7 +201,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   Work wk;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // 128 x 56 + 256 x 224 = 384 x 168;  128 x 56 + 384 x 152 = 512 x 128
   if (warp == 0) {
     // ============================== TMA producer ==============================
     int stage = 0;
@@ -329,13 +342,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if constexpr (kEpiWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     // ============================== epilogue (warps 4..11) ==============================
     // Math runs on packed fp32x2 (FFMA2): the fused epilogues are issue-bound, two columns per instruction.
     const avt_epilogue_t& ep = p.ep;
+    // EPI > 0: the hot ViT epilogues with everything but the bias decided at compile time (the generic body carries ~15
+    // uniform branches, both GELU flavours in four modes and the dropout / pos-embed / residual paths: 600 instructions
+    // per 32-column chunk where the specialised bodies need 300-450, and the fused-GELU epilogue is issue-bound)
+    constexpr bool kGen = EPI == kEpiGeneric;
+    const bool f_pos = kGen && ep.pos_period > 0;
+    const bool f_aux = kGen ? ep.aux_z != nullptr : EPI == kEpiGeluAux;
+    const bool f_dact = kGen ? ep.dact_z != nullptr : EPI == kEpiMulZ;
+    const bool f_drop = kGen && ep.drop_p > 0.f;
+    const bool f_res = kGen && ep.residual != nullptr;
+    const int f_tma_out = kGen ? p.tma_out : 1;
+    const bool f_tma_in = kGen ? p.tma_in != 0 : EPI == kEpiMulZ;
+    const int f_act = kGen ? ep.act : (EPI == kEpiGeluAux ? AVT_ACT_GELU_ERF : AVT_ACT_NONE);
+    const int f_aux_mode = kGen ? ep.aux_mode : 1;
+    const int f_dact_mode = kGen ? ep.dact_mode : 1;
     const int ew = warp - (2 + kSumWarps);
     const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the only ones this warp may read
-    const int chalf = ew >> 2;      // which half of the tile's columns this warp handles
+    const int cpart = ew >> 2;      // which part (half / third) of the tile's columns this warp handles
+    constexpr int kParts = kEpiWarps / 4, kChunks = BN / 32;
+    const int c_part_begin = 32 * (cpart * (kChunks / kParts) + min(cpart, kChunks % kParts));
+    const int c_part_end = c_part_begin + 32 * (kChunks / kParts + (cpart < kChunks % kParts ? 1 : 0));
     const int etid = threadIdx.x - 32 * (2 + kSumWarps);
     uint8_t* out_slots = sStageOut + ew * 4 * kSlotBytes;   // [2] staging for TMA stores
     uint8_t* in_slots = out_slots + 2 * kSlotBytes;         // [2] staging for TMA loads (dact_z)
@@ -343,10 +374,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t n_st = 0, n_in_issued = 0, n_in_waited = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+    const float keep_scale = f_drop ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
     // CUDA-graph friendly RNG: the per-step part of the Philox offset may live in device memory
-    const uint64_t drop_off = ep.drop_offset + ((ep.drop_p > 0.f && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
-    const bool scale_acc = ep.alpha != 1.0f;
+    const uint64_t drop_off = ep.drop_offset + ((f_drop && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
+    const bool scale_acc = kGen && ep.alpha != 1.0f;
     const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte offset (64 B rows)
 
     auto tma_store_chunk = [&](const CUtensorMap* tm, const float2* v, int col0, int row0) {
@@ -368,9 +399,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // 32 rows x 32 fp32 = 4 KB, 128-byte rows, SWIZZLE_128B (chunk ^= row & 7). Two buffers when the dact_z staging
       // slots are free (both out slots / both in slots): the next chunk is staged while the TMA drains this one - the
       // weight gradients of AVT-h (contraction over 80 rows) are nothing but this epilogue streaming 67 MB to HBM.
-      uint8_t* buf = out_slots + ((!p.tma_in && (n_st & 1)) ? 2 * kSlotBytes : 0);
+      uint8_t* buf = out_slots + ((!f_tma_in && (n_st & 1)) ? 2 * kSlotBytes : 0);
       if (lane == 0) {
-        if (p.tma_in) tma_store_wait_read<0>();
+        if (f_tma_in) tma_store_wait_read<0>();
         else tma_store_wait_read<1>();
       }
       __syncwarp();
@@ -404,27 +435,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m0 + quarter * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const int c_begin = chalf * (BN / 2);
-      const int c_end = min((chalf + 1) * (BN / 2), p.N - n0);  // N is a multiple of 32 (checked on host)
+      const int c_begin = c_part_begin;
+      const int c_end = min(c_part_end, p.N - n0);  // N is a multiple of 32 (checked on host)
       // stage this tile's bias slice in smem (one global read per column instead of one per row)
       float* bias_s = sBias + acc * BN;
       if (ep.bias) {
         for (int i = etid; i < BN; i += 32 * kEpiWarps) bias_s[i] = (n0 + i < p.N) ? __ldg(ep.bias + n0 + i) : 0.f;
       }
-      if (p.tma_in && c_begin < c_end) issue_in(n0 + c_begin, row0);
+      if (f_tma_in && c_begin < c_end) issue_in(n0 + c_begin, row0);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-      const int pos_t = ep.pos_period > 0 ? row % ep.pos_period : 0;
+      const int pos_t = f_pos ? row % ep.pos_period : 0;
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         const int col0 = n0 + c0;
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c0, r);
         uint4 zraw[4];
-        if (ep.dact_z) {
-          if (p.tma_in) {
+        if (f_dact) {
+          if (f_tma_in) {
             if (c0 + 32 < c_end) issue_in(col0 + 32, row0);
             const uint32_t sl = n_in_waited & 1;
             mbar_wait(&in_bar[sl], (n_in_waited >> 1) & 1);
@@ -456,7 +487,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[j + 1] = __fadd2_rn(v[j + 1], make_float2(b.z, b.w));
           }
         }
-        if (ep.pos_period > 0 && row_ok) {
+        if (f_pos && row_ok) {
           if (pos_t == 0 && ep.cls) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
@@ -473,14 +504,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[j + 1] = __fadd2_rn(v[j + 1], make_float2(b.z, b.w));
           }
         }
-        if (ep.aux_z) {
-          if (p.tma_out == 1) {
+        if (f_aux) {
+          if (f_tma_out == 1) {
             // act (and act') computed, packed and staged 16 bytes at a time; the saved tensor never sits in registers
             uint8_t* slot = out_slots + (n_st & 1) * kSlotBytes;
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
-            if (ep.aux_mode == 1) act_chunk_to_slot<2>(ep.act, v, slot + lane * 64, sw);  // save act'(pre-activation)
-            else act_chunk_to_slot<1>(ep.act, v, slot + lane * 64, sw);
+            if (f_aux_mode == 1) act_chunk_to_slot<2>(f_act, v, slot + lane * 64, sw);  // save act'(pre-activation)
+            else act_chunk_to_slot<1>(f_act, v, slot + lane * 64, sw);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -490,19 +521,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ++n_st;
           } else {
             float2 a[16];
-            if (ep.aux_mode == 1) act_chunk<2>(ep.act, v, a);  // save act'(pre-activation): backward only multiplies
-            else act_chunk<1>(ep.act, v, a);
+            if (f_aux_mode == 1) act_chunk<2>(f_act, v, a);  // save act'(pre-activation): backward only multiplies
+            else act_chunk<1>(f_act, v, a);
             if (row_ok) {
               uint4* zp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) zp[j] = pack8(a + 4 * j);
             }
           }
-        } else if (ep.act != AVT_ACT_NONE) {
+        } else if (f_act != AVT_ACT_NONE) {
           float2 unused[16];
-          act_chunk<0>(ep.act, v, unused);
+          act_chunk<0>(f_act, v, unused);
         }
-        if (ep.dact_z && (row_ok || p.tma_in)) {
+        if (f_dact && (row_ok || f_tma_in)) {
           float2 z[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -510,14 +541,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 4; ++q) z[4 * j + q] = make_float2(bf16_lo(zz[q]), bf16_hi(zz[q]));
           }
-          if (ep.dact_mode != 1) {
+          if (f_dact_mode != 1) {
             float2 unused[16];
             act_chunk<3>(ep.dact, z, unused);   // z <- dact'(z)
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __fmul2_rn(v[j], z[j]);
         }
-        if (ep.drop_p > 0.f) {
+        if (f_drop) {
           const uint64_t g0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)col0) >> 2;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -528,7 +559,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[2 * j + 1].y = (keep & 8u) ? v[2 * j + 1].y * keep_scale : 0.f;
           }
         }
-        if (ep.residual && row_ok) {
+        if (f_res && row_ok) {
           const float4* rp = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -537,9 +568,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[2 * j + 1] = __fadd2_rn(v[2 * j + 1], make_float2(b.z, b.w));
           }
         }
-        if (p.tma_out == 1) {
+        if (f_tma_out == 1) {
           tma_store_chunk(&tmOut, v, col0, row0);
-        } else if (p.tma_out == 2) {
+        } else if (f_tma_out == 2) {
           tma_store_chunk_f32(&tmOut, v, col0, row0);
         } else if (row_ok) {
           if (ep.out_fp32) {
@@ -715,10 +746,10 @@ struct GemmMaps {
   CUtensorMap a, b, out, aux, in;
 };
 
-template <int BN, int CG, bool A_MN, bool B_MN>
+template <int BN, int CG, bool A_MN, bool B_MN, int EPI = kEpiGeneric>
 static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
-  auto kern = gemm_bf16_kernel<BN, CG, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, CG, epi_warps(EPI)>;
+  auto kern = gemm_bf16_kernel<BN, CG, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     const int mx = Cfg::smem_bytes(true) > Cfg::smem_bytes(false) ? Cfg::smem_bytes(true) : Cfg::smem_bytes(false);
@@ -733,7 +764,7 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t 
   const int grid = CG * (units < groups ? units : groups);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = Cfg::smem_bytes(p.staging != 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -753,6 +784,12 @@ static int dispatch_major(int a_mn, int b_mn, const GemmMaps& tm, const GemmPara
   if (!a_mn && b_mn) return launch_gemm<BN, CG, false, true>(tm, p, s);
   if (a_mn && !b_mn) return launch_gemm<BN, CG, true, false>(tm, p, s);
   return launch_gemm<BN, CG, true, true>(tm, p, s);
+}
+// The specialised epilogues exist for the 256-wide CTA-pair kernel with a row-major A operand (every big ViT forward /
+// dgrad GEMM); B is [N, K] (nn.Linear forward) or [K, N] (dgrad).
+template <int EPI>
+static int dispatch_epi(int b_mn, const GemmMaps& tm, const GemmParams& p, cudaStream_t s) {
+  return b_mn ? launch_gemm<256, 2, false, true, EPI>(tm, p, s) : launch_gemm<256, 2, false, false, EPI>(tm, p, s);
 }
 
 }  // namespace avt
@@ -847,7 +884,17 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
       return rc;
   }
 
-  if (cta_group == 2) {
+  const avt_epilogue_t& e = p.ep;
+  const bool simple = cta_group == 2 && block_n == 256 && !a_mn && p.split_k == 1 && p.tma_out == 1 && e.alpha == 1.0f &&
+                      e.pos_period == 0 && e.drop_p == 0.f && !e.residual && !a_colsum && g_epi_special;
+  int epi = kEpiGeneric;
+  if (simple && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE) epi = kEpiStore;
+  else if (simple && e.aux_z && e.aux_mode == 1 && !e.dact_z && e.act == AVT_ACT_GELU_ERF) epi = kEpiGeluAux;
+  else if (simple && !e.aux_z && e.dact_z && e.dact_mode == 1 && e.act == AVT_ACT_NONE && !e.bias) epi = kEpiMulZ;
+  if (epi == kEpiStore) rc = dispatch_epi<kEpiStore>(b_mn, tm, p, s);
+  else if (epi == kEpiGeluAux) rc = dispatch_epi<kEpiGeluAux>(b_mn, tm, p, s);
+  else if (epi == kEpiMulZ) rc = dispatch_epi<kEpiMulZ>(b_mn, tm, p, s);
+  else if (cta_group == 2) {
     rc = block_n == 128 ? dispatch_major<128, 2>(a_mn, b_mn, tm, p, s) : dispatch_major<256, 2>(a_mn, b_mn, tm, p, s);
   } else {
     switch (block_n) {
@@ -864,5 +911,10 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     launch_kernel(epilogue_apply_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const float*>(workspace), p.split_k, (int)M, (int)N, finish);
     AVT_CUDA_OK(cudaGetLastError());
   }
+  return AVT_OK;
+}
+
+extern "C" int avt_set_gemm_specialized_epilogues(int enable) {
+  avt::g_epi_special = enable ? 1 : 0;
   return AVT_OK;
 }

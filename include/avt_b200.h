@@ -100,6 +100,11 @@ int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t l
                   int64_t K, const avt_epilogue_t* ep, int split_k, int block_n, int cta_group, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* The three hot ViT epilogues ([+bias] -> bf16; [+bias] + erf-GELU + saved derivative; x saved derivative) have
+ * compile-time specialised kernels (no run-time epilogue branches); 0 forces the generic kernel everywhere (A/B runs,
+ * and the parity tests run both). Default 1. */
+int avt_set_gemm_specialized_epilogues(int enable);
+
 /* Same GEMM, plus a_colsum[m] += sum_k A[m, k] (fp32 [M], atomics; NULL = off). Requires a_mn = 1. In a weight-gradient
  * GEMM dW = dY^T X the A operand is dY^T, so a_colsum is the bias gradient (column sums of dY): two extra warps add up
  * the A tiles that are in shared memory for the tensor core anyway, and the separate avt_colsum_bf16 pass over

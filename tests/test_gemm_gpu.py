@@ -241,3 +241,39 @@ def test_gemm_small_m_split_k_two_pass(b_mn):
     ops.gemm(a, b, o2, b_mn=b_mn, bias=bias, split_k=8, workspace=ws)
     _check(o1, pre, "fp32 tma store")
     _check(o2, pre, "fp32 two-pass")
+
+
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("kind", ["store", "store_bias", "gelu_aux", "mul_z"])
+def test_gemm_specialized_epilogues_match_generic(kind, b_mn):
+    """The compile-time specialised ViT epilogues (kEpiStore / kEpiGeluAux / kEpiMulZ, 256-wide CTA-pair kernel) must be
+    bit-identical to the generic run-time epilogue on the same inputs, and both must match the fp64 reference."""
+    ops = _ops()
+    from avt_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(41)
+    M, N, K = 1000, 768, 320                     # ragged M (4 pair tiles, the last one 232 rows), 3 N tiles, 5 k-blocks
+    a = _mk((M, K), g)
+    b = _mk((K, N) if b_mn else (N, K), g, 0.1)
+    bias = torch.randn(N, generator=g, device="cuda") if kind in ("store_bias", "gelu_aux") else None
+    z = _mk((M, N), g) if kind == "mul_z" else None
+    outs = []
+    for special in (1, 0):
+        _lib.lib().avt_set_gemm_specialized_epilogues(special)
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        aux = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16) if kind == "gelu_aux" else None
+        ops.gemm(a, b, out, b_mn=b_mn, bias=bias, act=1 if kind == "gelu_aux" else 0, aux_z=aux, aux_grad=aux is not None,
+                 dact_z=z, dact_is_grad=z is not None)
+        outs.append((out, aux))
+    _lib.lib().avt_set_gemm_specialized_epilogues(1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    pre = _ref(a, b, False, b_mn) + (bias.double() if bias is not None else 0.0)
+    if kind == "gelu_aux":
+        assert torch.equal(outs[0][1], outs[1][1])
+        want = torch.nn.functional.gelu(pre)
+        dwant = 0.5 * (1 + torch.erf(pre / 2 ** 0.5)) + pre * torch.exp(-pre * pre / 2) / (2 * torch.pi) ** 0.5
+        assert ((outs[0][1].double() - dwant).abs() <= 2.0**-7 * dwant.abs() + 1e-3).all()
+    elif kind == "mul_z":
+        want = pre * z.double()
+    else:
+        want = pre
+    assert ((outs[0][0].double() - want).abs() <= 2.0**-7 * want.abs() + 1e-3).all()
