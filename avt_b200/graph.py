@@ -34,9 +34,14 @@ class GraphedStep:
             self.static_output = fn(*self.static_inputs)
         self.avt_launches = _lib.launch_count - l0   # avt_* kernels inside one replay
 
-    def __call__(self, *inputs):
+    def __call__(self, *inputs, after_copy=None):
+        """Copy `inputs` into the static buffers, replay, return the static output. `after_copy()` runs between the input
+        copies and the replay (e.g. to record the event that lets a side stream refill a staging buffer while the step
+        computes: double-buffered input prefetch)."""
         for dst, src in zip(self.static_inputs, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+        if after_copy is not None:
+            after_copy()
         self.graph.replay()
         return self.static_output
