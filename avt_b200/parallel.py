@@ -45,12 +45,19 @@ class FlatDataParallel:
         self.vit, self.head = model.backbone.model, model.future_predictor
         self.vit.direct_grads = True
         self.head.direct_grads = True
-        self._handles = []
+        self._handles = []          # backbone slices + torch-owned rest
+        self._head_handles = []     # AVT-h flat buffer (issued first, finished first)
         self._layer_ranges = []
         self.head._grads_ready_hook = self._head_ready
         self.vit._grads_ready_hook = self._vit_ready
         self.other = [p for n, p in model.named_parameters()
                       if not n.startswith("backbone.model.") and not n.startswith("future_predictor.")]
+        # The torch-owned parameters (classifier) get their gradients at the very start of the backward: reduce them
+        # right there, under the whole AVT-h + backbone backward, instead of after it.
+        self._other_handles, self._other_early = [], set()
+        if self.comm_sms:
+            for p in self.other:
+                p.register_post_accumulate_grad_hook(self._other_ready)
 
     def broadcast_parameters(self):
         """DDP-constructor semantics: every rank starts from rank 0's weights (valid after the first forward)."""
@@ -58,10 +65,15 @@ class FlatDataParallel:
             for t in [self.vit.flat_buffers()[0], self.head.flat_buffers()[0]] + [p.data for p in self.other]:
                 dist.broadcast(t, 0, group=self.group)
 
+    def _other_ready(self, p):
+        if p.grad is not None:
+            self._other_early.add(id(p))
+            self._other_handles += allreduce_mean_([p.grad], self.group, async_op=True)
+
     def _head_ready(self):
         if self.comm_sms:
             _lib.lib().avt_set_sm_limit(_sm_count() - self.comm_sms)
-        self._handles += allreduce_mean_([self.head.flat_buffers()[1]], self.group, async_op=True)
+        self._head_handles += allreduce_mean_([self.head.flat_buffers()[1]], self.group, async_op=True)
 
     def _vit_layer_done(self, i):
         """Layer i's weight gradients are final: reduce that slice now, overlapped with the rest of the backward."""
@@ -86,13 +98,31 @@ class FlatDataParallel:
         self._layer_ranges = []
         self._handles += allreduce_mean_(rest, self.group, async_op=True)
 
-    def finish_backward(self):
-        """Call after loss.backward(): reduces the remaining (torch-owned) gradients and waits for all handles."""
-        grads = [p.grad for p in self.other if p.grad is not None]
-        self._handles += allreduce_mean_(grads, self.group, async_op=True)
+    def finish_backward(self, optimizer=None):
+        """Call after loss.backward(): reduces the remaining (torch-owned) gradients and waits for all handles.
+        With `optimizer` (an avt_b200.optim.FlatSGD over [backbone.model, future_predictor] + the other parameters) the
+        update is interleaved with the waits: the AVT-h buffer - reduced while the backbone backward ran - is updated
+        first (1.1 ms of HBM time), which hides the tail of the collective (last backbone slices, small tensors) that
+        would otherwise sit between the backward and the optimizer."""
+        grads = [p.grad for p in self.other if p.grad is not None and id(p) not in self._other_early]
+        other_handles = self._other_handles + allreduce_mean_(grads, self.group, async_op=True)
+        self._other_handles, self._other_early = [], set()
+        if optimizer is not None:
+            assert [m for m in optimizer.mods] == [self.vit, self.head], "FlatSGD([dp.vit, dp.head], dp.other, ...) expected"
+            optimizer.sync_lr()
+        for h in self._head_handles:
+            h.wait()
+        if optimizer is not None:
+            optimizer.step_flat(1)
         for h in self._handles:
             h.wait()
-        self._handles = []
+        if optimizer is not None:
+            optimizer.step_flat(0)
+        for h in other_handles:
+            h.wait()
+        if optimizer is not None:
+            optimizer.step_other()
+        self._handles, self._head_handles = [], []
         if self.comm_sms:
             _lib.lib().avt_set_sm_limit(0)
 

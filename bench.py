@@ -163,8 +163,7 @@ def run_ours(args):
         for p in dp.other:
             p.grad = None
         loss.backward()
-        dp.finish_backward()
-        state["opt"].step()
+        dp.finish_backward(state["opt"])     # waits for the collectives piecewise and applies the fused SGD in between
         return loss
 
     runner = {"fn": core, "graph": None, "note": "eager"}
