@@ -244,6 +244,48 @@ class AVTh(nn.Module):
             self._grads_ready_hook()
         return dfeats
 
+    def _run_rollout(self, feats2d, B, T, output_len):
+        """Autoregressive rollout for evaluation (reference :168-202: `output_len` GPT-2 calls, each fed the LAST hidden
+        state of the previous one with `past_key_values` and continuing position ids). Attention is causal and dropout
+        is off in eval mode, so call i of the KV-cached loop equals row T-1+i of ONE causal pass over the T+i embeddings
+        [encoder(feats) ; h_{T-1} ; ... ; h_{T+i-2}] + wpe[0 : T+i]: the rollout is run as output_len growing causal
+        passes over the forward kernels (<= 16 + output_len tokens: the stack is 80-row GEMMs either way), no KV cache to
+        manage. Returns decoded outputs [B, T + output_len - 1, C] (fp32). No autograd graph."""
+        pk, st = self._pack, self._stack
+        C, Dh = self.in_features, self.inter_dim
+        dev = feats2d.device
+        pk.refresh_bf16()
+        wpe = pk.wv("gpt_model.wpe.weight")
+        xb = torch.empty(B * T, C, dtype=torch.bfloat16, device=dev)
+        ops.cast_bf16(feats2d.contiguous().float(), xb)
+        emb = torch.empty(B * T, Dh, dtype=torch.float32, device=dev)           # encoder(feats) + wpe[:T]
+        sk = engine.small_m_split(B * T, Dh, C)
+        ops.gemm(xb, pk.bv("encoder.weight"), emb, pos=wpe[:T], pos_period=T, split_k=sk, workspace=st._gemm_ws(emb, sk))
+        seq = emb.view(B, T, Dh)
+        decoded_all = None
+        for i in range(output_len):
+            Ti = T + i
+            M = B * Ti
+            w = st.workspace(M, B, Ti, False)
+            w["x"][0].copy_(seq.reshape(M, Dh))
+            xmid, y = st.forward(w, B, Ti, False)
+            hid = torch.empty(M, Dh, dtype=torch.float32, device=dev)           # ln_f output, fp32 (fed back below)
+            ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, hid, add=y,
+                              x_out=st._xbuf(w, False, 2 * self.n_layer))
+            hid = hid.view(B, Ti, Dh)
+            new = hid if i == 0 else hid[:, -1:, :]                             # call 0 returns T states, later calls one
+            rows = new.reshape(-1, Dh)
+            hb = torch.empty(rows.shape[0], Dh, dtype=torch.bfloat16, device=dev)
+            ops.cast_bf16(rows.contiguous(), hb)
+            dec = torch.empty(rows.shape[0], C, dtype=torch.float32, device=dev)
+            sk = engine.small_m_split(rows.shape[0], C, Dh)
+            ops.gemm(hb, pk.bv("decoder.weight"), dec, split_k=sk, workspace=st._gemm_ws(dec, sk))
+            dec = dec.view(B, -1, C)
+            decoded_all = dec if decoded_all is None else torch.cat([decoded_all, dec], dim=1)
+            if i + 1 < output_len:   # next input embedding: last hidden state + wpe[position T + i]   (:202, position_ids :169-173)
+                seq = torch.cat([seq, hid[:, -1:, :] + wpe[Ti].view(1, 1, Dh)], dim=1)
+        return decoded_all
+
     # ------------------------------------------------------------------ reference-compatible forward
     def forward(self, feats, target_shape):
         if not feats.is_cuda:
@@ -256,15 +298,23 @@ class AVTh(nn.Module):
             output_len = self.output_len
         else:
             output_len = self.output_len_eval
-        if output_len != 1:
-            raise NotImplementedError("autoregressive rollout (output_len != 1) is an eval-only path; every shipped "
-                                      "AVT experiment trains and evaluates with output_len=1")
+        if output_len < 1:
+            raise NotImplementedError("output_len must be >= 1 (the reference's output_len <= 0 returns nothing to decode)")
         B, T, C = feats.shape
         self._ensure_pack(feats.device)
         full_orig_feats = inp_feats = feats
         orig_feats_len = T
         train_graph = torch.is_grad_enabled() and (feats.requires_grad or any(p.requires_grad for p in self._param_list))
-        decoded = _HeadFunction.apply(feats.reshape(B * T, C), self, B, T, train_graph, *self._param_list).view(B, T, C)
+        if output_len == 1:
+            decoded = _HeadFunction.apply(feats.reshape(B * T, C), self, B, T, train_graph, *self._param_list).view(B, T, C)
+        else:
+            if train_graph or self.training:
+                raise NotImplementedError("autoregressive rollout (output_len > 1) is implemented for evaluation "
+                                          "(model.eval() under torch.no_grad(), func/train.py:357); every shipped AVT "
+                                          "experiment trains with output_len=1")
+            if T + output_len - 1 > self.gpt_model.wpe.weight.shape[0]:
+                raise ValueError("rollout exceeds n_positions")
+            decoded = self._run_rollout(feats.reshape(B * T, C), B, T, output_len)
         all_outputs = decoded                                            # :227-229
         losses = {}
         if self.future_pred_loss is not None:                            # :207-215

@@ -279,3 +279,34 @@ def test_state_dict_load_after_first_forward_updates_kernels():
     ref = o_vit.create_model("vit_test_patch16_32")
     ref.load_state_dict({k: v.cpu() for k, v in sd.items()})
     assert not torch.equal(y0, y1) and rel(y1, ref(x.cpu())) <= OUT_TOL
+
+
+@pytest.mark.parametrize("C,Dh,nh,nl,B,T,olen,avg", [
+    (64, 128, 2, 3, 3, 6, 3, -1),          # small: 3-step rollout, every past + future feature returned
+    (768, 2048, 4, 6, 8, 10, 4, 1),        # expts/01 head, 4-step rollout at evaluation, last future feature only
+])
+def test_avth_eval_rollout_vs_oracle(C, Dh, nh, nl, B, T, olen, avg):
+    """autoregressive rollout at evaluation (reference future_prediction.py:168-202, KV-cached GPT-2
+    calls fed their own last hidden state). Ours runs it as growing causal passes; the oracle uses the KV cache."""
+    from avt_b200 import future_prediction as fp
+    torch.manual_seed(0)
+    kw = dict(output_len=1, output_len_eval=olen, inter_dim=Dh, n_head=nh, n_layer=nl, return_past_too=True, avg_last_n=avg)
+    ref = o_avth.AVTh(C, future_pred_loss="mse", **kw)
+    stress_init(ref)
+    ours = fp.AVTh(C, future_pred_loss={"_target_": "torch.nn.MSELoss"}, **kw)
+    ours.load_state_dict(ref.state_dict())
+    ours, ref = ours.cuda().eval(), ref.double().eval()
+    x = torch.randn(B, T, C, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        pr, fr, lr, _ = ref(x.double(), (B,))
+        po, fo, lo, _ = ours(x.cuda(), (B,))
+        # target_shape with 3 dims selects the rollout length explicitly (reference :123-124)
+        _, f2r, _, _ = ref(x.double(), (B, 2, C))
+        _, f2o, _, _ = ours(x.cuda(), (B, 2, C))
+    assert po.shape == pr.shape and fo.shape == fr.shape and lo["feat"].shape == lr["feat"].shape
+    assert fo.shape == ((B, C) if avg > 0 else (B, T + olen, C))
+    assert rel(po, pr) <= OUT_TOL and rel(fo, fr) <= 2 * OUT_TOL and rel(lo["feat"], lr["feat"]) <= OUT_TOL
+    assert rel(f2o, f2r) <= 2 * OUT_TOL
+    ours.train()
+    with pytest.raises(NotImplementedError):
+        ours(x.cuda(), (B, 2, C))
