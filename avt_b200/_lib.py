@@ -49,8 +49,6 @@ SIGNATURES = {
     "avt_check_device": [],
     "avt_set_sm_limit": [_i32],
     "avt_set_pdl": [_i32],
-    "avt_set_stream_k_tail": [_i32],
-    "avt_set_gemm_scratch": [_vp, _i64],
     "avt_set_gemm_specialized_epilogues": [_i32],
     "avt_gemm_bf16": [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(Epilogue), _i32, _i32, _i32, _vp, _i64,
                       _vp],

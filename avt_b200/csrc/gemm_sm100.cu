@@ -41,15 +41,7 @@ constexpr int kSlotBytes = 2048;  // TMA-store staging slot: 32 rows x 32 bf16 (
 constexpr int kSmemLimit = 227 * 1024;
 
 constexpr int kMaxStages = 8;
-static int g_epi_special = 1;
-// Off by default. Measured on B200 (tools/sweep.py streamk): with the fix-up hidden behind whole-tile main loops the
-// K = 3072 GEMMs do 16 % fewer k-block rounds per CTA pair and still take the same time (61.3 vs 60.5 us) - the chip runs
-// these kernels at its power cap (sw_power_cap, 1.7-1.85 GHz under load), so filling the idle partial round lowers the
-// clock instead of the time. avt_set_stream_k_tail(1) turns it on (the parity test does).
-static int g_stream_k_tail = 0;
-static void* sk_scratch = nullptr;      // avt_set_gemm_scratch(): zero-initialised device scratch for the stream-K tail
-static int64_t sk_scratch_bytes = 0;
-constexpr int64_t kSkCtrBytes = 65536;  // head of the scratch: per-slab arrival counters (zero between launches)   // avt_set_gemm_specialized_epilogues(0): always run the generic epilogue (A/B, tests)
+static int g_epi_special = 1;   // avt_set_gemm_specialized_epilogues(0): always run the generic epilogue (A/B, tests)
 template <int BN, int CG, int EW = 8>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
@@ -78,14 +70,6 @@ struct GemmParams {
   int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
   int split_slices;  // split-K partials go to out + split*M*ldo (deterministic two-pass) instead of atomics
   int stream_k;      // atomics path only: the tiles' k-blocks are dealt out as ONE contiguous range per CTA group
-  // Stream-K tail of the forward / dgrad GEMMs (fused epilogues): the last `sk_tiles` tiles (the partial last round of the
-  // persistent grid) are cut along K into equal contiguous k-block ranges, one per CTA group, processed BEFORE the whole
-  // tiles. The <= 5 contributors of a tail tile reduce-scatter it: every epilogue warp owns chunk c of its slab if
-  // c % nslices == its slice, dumps its other chunks into the fp32 workspace, waits for its peers (all co-resident, all
-  // in their first work item), adds their partials to the chunks it kept in TMEM and runs the fused epilogue on those.
-  int sk_tiles, sk_q, sk_slices;   // sk_slices: slices reserved per tail tile in the workspace
-  float* sk_ws;                    // [tail tile][slice][cta rank][epilogue warp][chunk][8][32] float4
-  unsigned int* sk_ctr;            // [tail tile][cta rank][epilogue warp][arrived, done]; zero between launches
   int stages;        // operand ring depth (GemmCfg::stages)
   int staging;       // TMA staging slots present in shared memory
   int k_rotate;      // producer walks each tile's k-blocks from a tile-dependent start
@@ -102,8 +86,6 @@ __device__ __forceinline__ uint4 pack8(const float2* v) {  // 4 float2 = 8 conse
 struct Work {
   int tile, kb0, kb1, split;
   bool shared;   // other groups contribute to the same tile: partial sums meet in fp32 atomics / workspace slices
-  int sk_tile;   // >= 0: stream-K tail segment of tail tile sk_tile; this group is contributor sk_slice of sk_n
-  int sk_slice, sk_n;
 };
 // Every warp role walks the same sequence. Uniform mode: units (tile, split) round-robin over the groups. Stream-K mode
 // (weight gradients: few tiles, very long K, fp32 atomics into the output): the tiles x k-blocks space is cut into one
@@ -111,37 +93,16 @@ struct Work {
 // SMs the grid was given (72 units on 74 CTA pairs waste 3 %; on the 70 pairs left beside an NCCL all-reduce they would
 // need two rounds).
 struct WorkIter {
-  int ngroups, group, unit, pos, end;
-  __device__ WorkIter(const GemmParams& p, int group_, int ngroups_)
-      : ngroups(ngroups_), group(group_), unit(group_), pos(0), end(0) {
+  int ngroups, unit, pos, end;
+  __device__ WorkIter(const GemmParams& p, int group, int ngroups_) : ngroups(ngroups_), unit(group), pos(0), end(0) {
     if (p.stream_k) {
       const int total = p.num_m_tiles * p.num_n_tiles * p.num_k_blocks;
       const int q = (total + ngroups - 1) / ngroups;
       pos = min(group * q, total);
       end = min(pos + q, total);
-    } else if (p.sk_tiles > 0) {
-      const int total = p.sk_tiles * p.num_k_blocks;
-      pos = min(group * p.sk_q, total);
-      end = min(pos + p.sk_q, total);
     }
   }
   __device__ __forceinline__ bool next(const GemmParams& p, Work& w) {
-    w.sk_tile = -1;
-    if (p.sk_tiles > 0 && pos < end) {   // tail segment: k-blocks [kb0, kb1) of tail tile t
-      const int nkb = p.num_k_blocks;
-      const int t = pos / nkb;
-      w.kb0 = pos - t * nkb;
-      w.kb1 = min(nkb, w.kb0 + (end - pos));
-      w.tile = p.num_m_tiles * p.num_n_tiles - p.sk_tiles + t;
-      w.split = 0;
-      const int first = (t * nkb) / p.sk_q, last = ((t + 1) * nkb - 1) / p.sk_q;
-      w.sk_n = last - first + 1;
-      w.sk_slice = group - first;
-      w.sk_tile = w.sk_n > 1 ? t : -1;
-      w.shared = false;
-      pos += w.kb1 - w.kb0;
-      return true;
-    }
     if (p.stream_k) {
       if (pos >= end) return false;
       const int nkb = p.num_k_blocks;
@@ -153,7 +114,7 @@ struct WorkIter {
       pos += w.kb1 - w.kb0;
       return true;
     }
-    if (unit >= (p.num_m_tiles * p.num_n_tiles - p.sk_tiles) * p.split_k) return false;
+    if (unit >= p.num_m_tiles * p.num_n_tiles * p.split_k) return false;
     w.tile = unit / p.split_k;
     w.split = unit % p.split_k;
     w.kb0 = w.split * p.kb_per_split;
@@ -240,7 +201,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   Work wk;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // 128 x 64 + 256 x 216 <= 384 x 168;  128 x 64 + 384 x 144 <= 512 x 128
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // 128 x 56 + 256 x 224 = 384 x 168;  128 x 56 + 384 x 152 = 512 x 128
   if (warp == 0) {
     // ============================== TMA producer ==============================
     int stage = 0;
@@ -381,8 +342,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   } else {
-    if constexpr (kEpiWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+    if constexpr (kEpiWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     // ============================== epilogue (warps 4..11) ==============================
     // Math runs on packed fp32x2 (FFMA2): the fused epilogues are issue-bound, two columns per instruction.
     const avt_epilogue_t& ep = p.ep;
@@ -466,73 +427,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ++n_in_issued;
     };
 
-    // Work items are finished as "jobs". A whole tile is one job, run as soon as its accumulator is complete. A stream-K
-    // tail segment is split in two: as soon as its accumulator is complete the warp dumps its slab into the workspace,
-    // posts its arrival and frees the accumulator (nothing here waits for anybody, so arrivals depend only on a group's own
-    // MMAs - a group whose k-range straddles two tail tiles must not let the second arrival wait for the first fix-up, or
-    // the fix-ups of all groups serialise into one chain - and the MMA warp is already on the next whole tile); the job
-    // that waits for the peers, sums the slices of the chunks this warp owns (c % nslices == slice) in slice order and
-    // runs the fused epilogue on them follows once ALL of this group's segments (at most two) have arrived.
-    Work pend0 = wk, pend1 = wk;                                // (named, not an array: they stay in registers)
-    int pacc0 = 0, pacc1 = 0;
-    int npend = 0;
-    uint32_t nb = 0;                                            // jobs so far (bias staging buffer = nb & 1)
-    constexpr int kSlabFloats = 32 * (BN / kParts);             // one warp's slab of one slice in the workspace
-    const size_t sk_slice_stride = (size_t)CG * kEpiWarps * kSlabFloats;
-    WorkIter it(p, group, ngroups);
-    while (true) {
-      const bool have = it.next(p, wk);
-      if (have && wk.sk_tile >= 0) {
-        // ---- tail segment, part 1: dump + arrive
-        const int m0 = (wk.tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
-        const int n0 = (wk.tile % p.num_n_tiles) * BN;
-        const int row0 = m0 + quarter * 32;
-        const int c_begin = c_part_begin;
-        const int c_end = min(c_part_end, p.N - n0);
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after_sync();
-        if (row0 < p.M && c_begin < c_end) {
-          const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-          const size_t slab0 = (((size_t)wk.sk_tile * p.sk_slices) * CG + rank) * kEpiWarps + ew;
-          float* mine = p.sk_ws + slab0 * kSlabFloats + (size_t)wk.sk_slice * sk_slice_stride + lane * 4;
-#pragma unroll 1
-          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_row + c0, r);
-            tmem_ld_wait();
-            float* d = mine + (c0 - c_begin) * 32;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              __stcg(reinterpret_cast<float4*>(d + j * 128),
-                     make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                 __uint_as_float(r[4 * j + 3])));
-          }
-          __threadfence();   // every lane: its partial sums are visible device-wide before the arrival is counted
-          __syncwarp();
-          if (lane == 0) atomicAdd(p.sk_ctr + (((size_t)wk.sk_tile * CG + rank) * kEpiWarps + ew) * 2, 1u);
-        }
-        // the accumulator is free again: the MMA warp moves on to whole tiles while the fix-up below waits for the peers
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[acc], 0);
-          else mbar_arrive(&tempty_bar[acc]);
-        }
-        if (npend == 0) { pend0 = wk; pacc0 = acc; }
-        else { pend1 = wk; pacc1 = acc; }
-        ++npend;
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-        continue;
-      }
-      const int njobs = npend + (have ? 1 : 0);
-#pragma unroll 1
-      for (int jb = 0; jb < njobs; ++jb) {
-      const bool sk = jb < npend;
-      const Work jw = sk ? (jb == 0 ? pend0 : pend1) : wk;
-      const int jacc = sk ? (jb == 0 ? pacc0 : pacc1) : acc;
-      const int tile = jw.tile;
-      const int split = jw.split;
+    for (WorkIter it(p, group, ngroups); it.next(p, wk);) {
+      const int tile = wk.tile;
+      const int split = wk.split;
       const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
       const int row0 = m0 + quarter * 32;
@@ -541,53 +438,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int c_begin = c_part_begin;
       const int c_end = min(c_part_end, p.N - n0);  // N is a multiple of 32 (checked on host)
       // stage this tile's bias slice in smem (one global read per column instead of one per row)
-      float* bias_s = sBias + (nb & 1) * BN;
-      ++nb;
+      float* bias_s = sBias + acc * BN;
       if (ep.bias) {
         for (int i = etid; i < BN; i += 32 * kEpiWarps) bias_s[i] = (n0 + i < p.N) ? __ldg(ep.bias + n0 + i) : 0.f;
       }
-      // stream-K tail segment: this warp finishes only the chunks c0 = c_first, c_first + c_step, ... of its slab
-      const int c_step = sk ? 32 * jw.sk_n : 32;
-      const int c_first = c_begin + (sk ? 32 * jw.sk_slice : 0);
-      if (f_tma_in && c_first < c_end) issue_in(n0 + c_first, row0);
+      if (f_tma_in && c_begin < c_end) issue_in(n0 + c_begin, row0);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      if (!sk) {
-        mbar_wait(&tfull_bar[jacc], acc_phase);
-        tc_fence_after_sync();
-      }
-      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + jacc * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
       const int pos_t = f_pos ? row % ep.pos_period : 0;
-      const float* sk_peer = nullptr;                          // slab of slice 0 of this (tile, rank, warp)
-      unsigned int* sk_ctr = nullptr;
-      if (sk && row0 < p.M && c_begin < c_end) {               // (the same condition for every contributor of the tile)
-        const size_t slab0 = (((size_t)jw.sk_tile * p.sk_slices) * CG + rank) * kEpiWarps + ew;
-        sk_peer = p.sk_ws + slab0 * kSlabFloats + lane * 4;
-        sk_ctr = p.sk_ctr + (((size_t)jw.sk_tile * CG + rank) * kEpiWarps + ew) * 2;
-        if (lane == 0) {
-          // peers are co-resident CTAs working on their own tail segments (the grid never exceeds the SMs it was given)
-          unsigned int seen;
-          uint32_t spins = 0;
-          uint64_t t0 = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sk_ctr) : "memory");
-            if (seen < (unsigned)jw.sk_n && (++spins & 0x3FFu) == 0) {
-              const uint64_t t = global_timer_ns();
-              if (t0 == 0) t0 = t;
-              else if (t - t0 > AVT_WATCHDOG_NS) __trap();
-            }
-          } while (seen < (unsigned)jw.sk_n);
-        }
-        __syncwarp();
-      }
 #pragma unroll 1
-      for (int c0 = c_first; c0 < c_end; c0 += c_step) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         const int col0 = n0 + c0;
         uint32_t r[32];
-        if (!sk) tmem_ld_32x32b_x32(t_row + c0, r);
+        tmem_ld_32x32b_x32(t_row + c0, r);
         uint4 zraw[4];
         if (f_dact) {
           if (f_tma_in) {
-            if (c0 + c_step < c_end) issue_in(col0 + c_step, row0);
+            if (c0 + 32 < c_end) issue_in(col0 + 32, row0);
             const uint32_t sl = n_in_waited & 1;
             mbar_wait(&in_bar[sl], (n_in_waited >> 1) & 1);
             const uint8_t* slot = in_slots + sl * kSlotBytes + lane * 64;
@@ -602,35 +471,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 4; ++j) zraw[j] = __ldg(zp + j);
           }
         }
+        tmem_ld_wait();
         float2 v[16];
-        if (!sk) {
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        } else if (sk_peer != nullptr) {   // the slices of this chunk (own one included), added in slice order: bit-reproducible
-          const float* src = sk_peer + (c0 - c_begin) * 32;
-          float4 t[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = __ldcg(reinterpret_cast<const float4*>(src + j * 128));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[2 * j] = make_float2(t[j].x, t[j].y);
-            v[2 * j + 1] = make_float2(t[j].z, t[j].w);
-          }
-          for (int sl = 1; sl < jw.sk_n; ++sl) {
-            src += sk_slice_stride;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = __ldcg(reinterpret_cast<const float4*>(src + j * 128));
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] = __fadd2_rn(v[2 * j], make_float2(t[j].x, t[j].y));
-              v[2 * j + 1] = __fadd2_rn(v[2 * j + 1], make_float2(t[j].z, t[j].w));
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
-        }
+        for (int j = 0; j < 16; ++j) v[j] = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
         if (scale_acc) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __fmul2_rn(v[j], f2(ep.alpha));
@@ -736,7 +580,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
-            } else if (jw.shared) {
+            } else if (wk.shared) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 atomicAdd(reinterpret_cast<float4*>(op + 4 * j), make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y));
@@ -762,20 +606,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if (!sk) {
-          if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[jacc], 0);  // the leader's barrier collects both CTAs
-          else mbar_arrive(&tempty_bar[jacc]);
-        }
-        if (sk_ctr != nullptr) {   // the last contributor to leave re-arms the counters for the next launch
-          if (atomicAdd(sk_ctr + 1, 1u) == (unsigned)jw.sk_n - 1) {
-            sk_ctr[0] = 0u;
-            sk_ctr[1] = 0u;
-          }
-        }
+        if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's barrier collects both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
       }
-      }  // jobs
-      npend = 0;
-      if (!have) break;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -1027,35 +860,6 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     p.ep.ldo = N;
     p.ep.out_fp32 = 1;
   }
-  // stream-K tail (see GemmParams): only with a caller-supplied scratch, on full persistent grids with a partial last round
-  p.sk_tiles = 0;
-  p.sk_q = 1;
-  p.sk_slices = 1;
-  p.sk_ws = nullptr;
-  p.sk_ctr = nullptr;
-  {
-    const int tiles = p.num_m_tiles * p.num_n_tiles, groups = num_sms() / cta_group, nkb = p.num_k_blocks;
-    if (g_stream_k_tail && sk_scratch && p.split_k == 1 && tiles > groups && tiles % groups != 0 && nkb >= 24) {
-      const int r = tiles % groups;
-      int q = (r * nkb + groups - 1) / groups;
-      const int q_min = (nkb + 3) / 4;                       // <= 5 contributors per tile
-      if (q < q_min) q = q_min;
-      int max_sl = 1;
-      for (int t = 0; t < r; ++t) {
-        const int sl = ((t + 1) * nkb - 1) / q - (t * nkb) / q + 1;
-        if (sl > max_sl) max_sl = sl;
-      }
-      const int64_t need = kSkCtrBytes + (int64_t)r * max_sl * cta_group * kBM * block_n * 4;
-      if (q * 10 <= nkb * 8 && max_sl > 1 && need <= sk_scratch_bytes &&
-          (int64_t)r * cta_group * 8 * 2 * 4 <= kSkCtrBytes) {
-        p.sk_tiles = r;
-        p.sk_q = q;
-        p.sk_slices = max_sl;
-        p.sk_ctr = reinterpret_cast<unsigned int*>(sk_scratch);
-        p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sk_scratch) + kSkCtrBytes);
-      }
-    }
-  }
   p.tma_out = p.split_k > 1 ? 0 : (!p.ep.out_fp32 ? 1 : (p.ep.accumulate ? 0 : 2));
   p.tma_in = p.ep.dact_z ? 1 : 0;
 
@@ -1107,21 +911,6 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     launch_kernel(epilogue_apply_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const float*>(workspace), p.split_k, (int)M, (int)N, finish);
     AVT_CUDA_OK(cudaGetLastError());
   }
-  return AVT_OK;
-}
-
-extern "C" int avt_set_stream_k_tail(int enable) {
-  avt::g_stream_k_tail = enable ? 1 : 0;
-  return AVT_OK;
-}
-
-extern "C" int avt_set_gemm_scratch(void* scratch, int64_t bytes) {
-  if (scratch && ((reinterpret_cast<uintptr_t>(scratch) & 255) != 0 || bytes < avt::kSkCtrBytes)) {
-    avt::set_last_error("avt_set_gemm_scratch", "scratch must be 256-byte aligned and hold at least 64 KB", __FILE__, __LINE__);
-    return AVT_ERR_INVALID;
-  }
-  avt::sk_scratch = scratch;
-  avt::sk_scratch_bytes = scratch ? bytes : 0;
   return AVT_OK;
 }
 

@@ -43,7 +43,6 @@ class ParamPack:
             self.small_end = 0
         self.total = off
         self.device = device
-        ops.ensure_gemm_scratch(device)
         self.w = torch.zeros(off, dtype=torch.float32, device=device)
         self.g = torch.zeros(off, dtype=torch.float32, device=device)
         self.b = torch.zeros(off, dtype=torch.bfloat16, device=device)

@@ -24,23 +24,6 @@ def _chk_cuda(*ts):
             raise RuntimeError("avt_b200 ops need CUDA tensors (there is no CPU path)")
 
 
-_GEMM_SCRATCH = {}
-
-
-def ensure_gemm_scratch(device, nbytes=96 << 20):
-    """Register (once per device) the zero-initialised scratch the stream-K tail of the big GEMMs reduces through
-    (avt_set_gemm_scratch). Called by the engine before its first GEMM."""
-    dev = torch.device(device)
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    buf = _GEMM_SCRATCH.get(idx)
-    if buf is None:
-        buf = torch.zeros(nbytes, dtype=torch.uint8, device=torch.device("cuda", idx))
-        _GEMM_SCRATCH[idx] = buf
-        _lib.call("avt_set_gemm_scratch", C.c_void_p(buf.data_ptr()), buf.numel())
-        _lib.launch_count -= 1      # not a kernel launch
-    return buf
-
-
 def small_m_block_n(N):
     """Tile width of the weight-streaming GEMMs (AVT-h, M = B*T <= 128 rows). Measured on B200 (tools/sweep.py head):
     128-wide tiles (256-byte weight rows per TMA box) + split-K beat 64-wide ones once N >= 2048."""

@@ -105,18 +105,6 @@ int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t l
  * and the parity tests run both). Default 1. */
 int avt_set_gemm_specialized_epilogues(int enable);
 
-/* Stream-K tail of the big forward / dgrad GEMMs. A persistent grid of G CTA groups needs ceil(tiles / G) rounds: the
- * 186 (256 x 256) tiles of timm Mlp.fc2 at the BASELINE shape cost 3 rounds on 74 CTA pairs for 2.51 rounds of work.
- * With a scratch buffer registered here (zero-initialised by the caller, >= 64 KB + tail tiles x slices x tile bytes;
- * 96 MB covers every ViT-B/L shape) the last tiles % G tiles are cut along K into equal contiguous k-block ranges, one
- * per group, processed first; their <= 5 contributors reduce-scatter the tile through the scratch inside the kernel
- * (partials added in slice order: bit-reproducible) and run the fused epilogue on their share. The first 64 KB are
- * arrival counters that every launch leaves zero. One scratch per process / device, used by the GEMMs of one stream at
- * a time. Off by default - avt_set_stream_k_tail(1) enables it: on B200 these GEMMs run at the power cap, and doing 16 %
- * fewer k-block rounds per CTA pair did not shorten them; the parity tests run both schedules. */
-int avt_set_gemm_scratch(void* scratch, int64_t bytes);
-int avt_set_stream_k_tail(int enable);
-
 /* Same GEMM, plus a_colsum[m] += sum_k A[m, k] (fp32 [M], atomics; NULL = off). Requires a_mn = 1. In a weight-gradient
  * GEMM dW = dY^T X the A operand is dY^T, so a_colsum is the bias gradient (column sums of dY): two extra warps add up
  * the A tiles that are in shared memory for the tensor core anyway, and the separate avt_colsum_bf16 pass over

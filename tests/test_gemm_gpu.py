@@ -277,47 +277,3 @@ def test_gemm_specialized_epilogues_match_generic(kind, b_mn):
     else:
         want = pre
     assert ((outs[0][0].double() - want).abs() <= 2.0**-7 * want.abs() + 1e-3).all()
-
-
-@pytest.mark.parametrize("M,N,K,kw", [
-    (15760, 3072, 768, dict(act=1, aux=True)),       # timm Mlp.fc1 at the BASELINE shape: 744 pair tiles on 74 pairs, 4 tail tiles
-    (15760, 768, 3072, dict()),                      # fc2: 186 tiles, 38 tail tiles x 48 k-blocks, <= 3 contributors per tile
-    (15760, 3072, 768, dict(b_mn=True, dact=True)),  # fc2 dgrad layout + gelu' operand through the TMA-in path
-    (15760, 768, 2304, dict(b_mn=True)),             # qkv dgrad layout
-    (15760, 768, 768, dict(residual=True)),          # generic kernel, fp32 output with residual
-    (23640, 1024, 1024, dict()),                     # ViT-L proj at T = 15: ragged M, 4 N tiles
-])
-def test_gemm_stream_k_tail(M, N, K, kw):
-    """Stream-K tail of the big GEMMs (last partial round cut along K, reduce-scatter fix-up through the registered scratch)
-    must reproduce the plain persistent schedule: identical whole tiles, tail tiles equal up to the fp32 order of <= 5
-    partial sums, bit-reproducible from run to run, arrival counters back to zero."""
-    ops = _ops()
-    from avt_b200 import _lib
-    g = torch.Generator(device="cuda").manual_seed(31)
-    b_mn = kw.get("b_mn", False)
-    a = _mk((M, K), g)
-    b = _mk((K, N) if b_mn else (N, K), g, 0.03)
-    bias = torch.randn(N, generator=g, device="cuda") if not kw.get("dact") else None
-    res = torch.randn(M, N, generator=g, device="cuda") if kw.get("residual") else None
-    z = _mk((M, N), g) if kw.get("dact") else None
-    scratch = ops.ensure_gemm_scratch("cuda")
-    outs = []
-    for tail in (0, 1, 1):
-        _lib.lib().avt_set_stream_k_tail(tail)     # (off by default: see gemm_sm100.cu)
-        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if res is not None else torch.bfloat16)
-        aux = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16) if kw.get("aux") else None
-        ops.gemm(a, b, out, b_mn=b_mn, bias=bias, act=kw.get("act", 0), aux_z=aux, aux_grad=aux is not None, residual=res,
-                 dact_z=z, dact_is_grad=z is not None)
-        outs.append((out, aux))
-    _lib.lib().avt_set_stream_k_tail(0)
-    torch.cuda.synchronize()
-    assert int(scratch[:65536].view(torch.int32).abs().sum()) == 0            # counters re-armed
-    assert torch.equal(outs[1][0], outs[2][0])                                 # bit-reproducible
-    ref = outs[0][0].double()
-    assert torch.isfinite(outs[1][0]).all()
-    err = (outs[1][0].double() - ref).abs()
-    tol = 2.0**-7 * ref.abs() + 1e-3 if outs[0][0].dtype == torch.bfloat16 else 1e-5 * ref.abs() + 1e-4
-    assert (err <= tol).all(), float(err.max())
-    assert (outs[1][0] == outs[0][0]).double().mean().item() > 0.75            # whole tiles untouched
-    if kw.get("aux"):
-        assert ((outs[1][1].double() - outs[0][1].double()).abs() <= 2.0**-7 * outs[0][1].double().abs() + 1e-3).all()

@@ -156,40 +156,6 @@ def fc1():
         print(f"{name:28s} {t:7.1f} us {fl / t / 1e6:7.1f} TF/s", flush=True)
 
 
-def streamk():
-    """Every big ViT-B GEMM of one layer (fwd + dgrad), plain persistent schedule vs stream-K tail."""
-    from avt_b200 import _lib
-    M = 15760
-    ops.ensure_gemm_scratch(dev)
-    shapes = [("qkv fwd", 2304, 768, False, {}), ("proj fwd", 768, 768, False, {}), ("fc1 fwd gelu+aux", 3072, 768, False, "fc1"),
-              ("fc2 fwd", 768, 3072, False, {}), ("fc2 dgrad*gelu'", 3072, 768, True, "dact"), ("fc1 dgrad", 768, 3072, True, {}),
-              ("proj dgrad", 768, 768, True, {}), ("qkv dgrad", 768, 2304, True, {})]
-    tot = [0.0, 0.0]
-    for name, N, K, b_mn, kw in shapes:
-        a = rnd(M, K)
-        w = rnd(K, N, scale=0.03) if b_mn else rnd(N, K, scale=0.03)
-        out = torch.empty(M, N, device=dev, dtype=bf)
-        bias = torch.randn(N, device=dev)
-        z = torch.empty(M, N, device=dev, dtype=bf)
-        if kw == "fc1":
-            kw = dict(bias=bias, act=1, aux_z=z, aux_grad=True)
-        elif kw == "dact":
-            z = rnd(M, N)
-            kw = dict(dact_z=z, dact_is_grad=True)
-        else:
-            kw = dict(bias=bias) if not b_mn else {}
-        ts = []
-        for on in (0, 1):
-            _lib.lib().avt_set_stream_k_tail(on)
-            ts.append(timeit(lambda: ops.gemm(a, w, out, b_mn=b_mn, **kw)))
-        tot[0] += ts[0]; tot[1] += ts[1]
-        fl = 2.0 * M * N * K
-        print(f"{name:18s} N{N:<5d} K{K:<5d} plain {ts[0]:7.1f} us {fl / ts[0] / 1e6:7.1f} TF/s | stream-K tail {ts[1]:7.1f} us "
-              f"{fl / ts[1] / 1e6:7.1f} TF/s", flush=True)
-    _lib.lib().avt_set_stream_k_tail(0)
-    print(f"sum: plain {tot[0]:.1f} us, stream-K tail {tot[1]:.1f} us")
-
-
 if __name__ == "__main__":
     todo = sys.argv[1:] or ["wgrad", "head", "ln", "attn", "fc1"]
     print(torch.cuda.get_device_name(0))
