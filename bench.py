@@ -327,11 +327,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus,
-                         "traffic": 98.5e6, "kernel": "gemm_bf16_kernel (tcgen05), ViT GEMMs (M = 15 760 rows)",
+                         "traffic": 115.4e6, "kernel": "gemm_bf16_kernel (tcgen05), ViT GEMMs (M = 15 760 rows)",
                          "peak_source": f"{src} bf16_tflops_sustained",
                          "how": "sum of 2*M*N*K over the ViT GEMM launches of one step / sum of their CUDA-event durations",
                          "traffic_source": "profiles/r01_step_launches.md: ncu dram__bytes_read+write, mean per launch of the "
-                                           "172 ViT GEMM launches of one step (algorithmic operand+output bytes: 97 MB)",
+                                           "146 ViT GEMM launches of one step (algorithmic operand+output bytes: 117.6 MB)",
                          "launches": len(vit_events), "gemm_ms_per_step": gemm_ms, "step_achieved": step_tf,
                          "step_frac": (step_tf / sus) if step_tf else None},
             "attention": {"achieved": attn_tf, "unit": "TFLOP/s", "peak": sus, "frac": attn_tf / sus, "ms_per_step": attn_ms,
