@@ -130,6 +130,7 @@ constexpr int kEpiGeneric = 0;   // everything avt_epilogue_t can express, decid
 constexpr int kEpiStore = 1;     // [+ bias] -> bf16, TMA store                              (qkv / proj / fc2, plain dgrads)
 constexpr int kEpiGeluAux = 2;   // [+ bias], erf-GELU and its derivative -> two bf16 TMA stores (timm Mlp.fc1 forward)
 constexpr int kEpiMulZ = 3;      // x saved gelu' (TMA-loaded) -> bf16, TMA store               (fc2 dgrad through the GELU)
+constexpr int kEpiAtomic = 4;    // fp32 atomics into the output (stream-K weight gradients, both operands MN-major)
 
 template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
@@ -356,7 +357,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool f_dact = kGen ? ep.dact_z != nullptr : EPI == kEpiMulZ;
     const bool f_drop = kGen && ep.drop_p > 0.f;
     const bool f_res = kGen && ep.residual != nullptr;
-    const int f_tma_out = kGen ? p.tma_out : 1;
+    const int f_tma_out = kGen ? p.tma_out : (EPI == kEpiAtomic ? 0 : 1);
+    const bool f_out_fp32 = kGen ? ep.out_fp32 != 0 : EPI == kEpiAtomic;
+    const bool f_slices = kGen && p.split_slices != 0;
     const bool f_tma_in = kGen ? p.tma_in != 0 : EPI == kEpiMulZ;
     const int f_act = kGen ? ep.act : (EPI == kEpiGeluAux ? AVT_ACT_GELU_ERF : AVT_ACT_NONE);
     const int f_aux_mode = kGen ? ep.aux_mode : 1;
@@ -573,14 +576,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else if (f_tma_out == 2) {
           tma_store_chunk_f32(&tmOut, v, col0, row0);
         } else if (row_ok) {
-          if (ep.out_fp32) {
+          if (f_out_fp32) {
             float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-            if (p.split_slices) {
+            if (f_slices) {
               op += (size_t)split * p.M * ep.ldo;
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
-            } else if (wk.shared) {
+            } else if (kGen ? wk.shared : true) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 atomicAdd(reinterpret_cast<float4*>(op + 4 * j), make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y));
@@ -891,7 +894,11 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
   if (simple && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE) epi = kEpiStore;
   else if (simple && e.aux_z && e.aux_mode == 1 && !e.dact_z && e.act == AVT_ACT_GELU_ERF) epi = kEpiGeluAux;
   else if (simple && !e.aux_z && e.dact_z && e.dact_mode == 1 && e.act == AVT_ACT_NONE && !e.bias) epi = kEpiMulZ;
-  if (epi == kEpiStore) rc = dispatch_epi<kEpiStore>(b_mn, tm, p, s);
+  if (g_epi_special && cta_group == 2 && block_n == 256 && a_mn && b_mn && p.stream_k && !p.split_slices && e.alpha == 1.0f &&
+      !e.bias && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE && e.drop_p == 0.f && !e.residual && e.pos_period == 0)
+    epi = kEpiAtomic;
+  if (epi == kEpiAtomic) rc = launch_gemm<256, 2, true, true, kEpiAtomic>(tm, p, s);
+  else if (epi == kEpiStore) rc = dispatch_epi<kEpiStore>(b_mn, tm, p, s);
   else if (epi == kEpiGeluAux) rc = dispatch_epi<kEpiGeluAux>(b_mn, tm, p, s);
   else if (epi == kEpiMulZ) rc = dispatch_epi<kEpiMulZ>(b_mn, tm, p, s);
   else if (cta_group == 2) {
