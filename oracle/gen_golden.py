@@ -54,6 +54,26 @@ def gen_avth():
     print("avth:", sum(v.numel() for v in sd.values()), "params")
 
 
+def gen_avth_rollout():
+    """Evaluation-time autoregressive rollout (reference future_prediction.py:168-202, KV-cached HF GPT-2 calls): 3 steps,
+    every past + predicted feature returned (avg_last_n = -1)."""
+    torch.manual_seed(0)
+    cfg = dict(output_len=1, output_len_eval=3, inter_dim=64, n_head=2, n_layer=2, n_positions=32, return_past_too=True,
+               avg_last_n=-1, future_pred_loss={"_target_": "torch.nn.MSELoss"}, future_pred_loss_wt=1.0)
+    m = ref_host.build_reference_avth(64, **cfg)
+    _stress(m, 11)
+    m.eval()
+    B, T = 3, 6
+    x = torch.randn(B, T, 64, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        past, fut, losses, _ = m(x, (B,))
+        _, fut2, _, _ = m(x, (B, 2, 64))          # 3-d target_shape selects the rollout length (:123-124)
+    sd = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
+    torch.save(dict(cfg={k: v for k, v in cfg.items() if k != "future_pred_loss"}, in_features=64, state=sd, x=x, past=past,
+                    future=fut, feat=losses["feat"], future_len2=fut2), os.path.join(OUT, "avth_rollout_ref_small.pt"))
+    print("avth rollout:", tuple(fut.shape), tuple(fut2.shape))
+
+
 def gen_basemodel():
     torch.manual_seed(0)
     head = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32)
@@ -78,4 +98,5 @@ if __name__ == "__main__":
     assert ref_host.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     gen_avth()
+    gen_avth_rollout()
     gen_basemodel()

@@ -165,6 +165,22 @@ def test_avth_matches_reference_golden():
             assert rel(p.grad, g["grads"][n]) <= GRAD_TOL, n
 
 
+def test_avth_rollout_matches_reference_golden():
+    """Evaluation rollout vs golden vectors of the UNMODIFIED reference AVTh (HF GPT-2 with its KV cache)."""
+    from avt_b200 import future_prediction as fp
+    g = torch.load(os.path.join(GOLDEN, "avth_rollout_ref_small.pt"))
+    m = fp.AVTh(g["in_features"], future_pred_loss={"_target_": "torch.nn.MSELoss"}, **g["cfg"])
+    m.load_state_dict(g["state"])
+    m.cuda().eval()
+    x = g["x"].cuda()
+    with torch.no_grad():
+        past, fut, losses, _ = m(x, (x.shape[0],))
+        _, fut2, _, _ = m(x, (x.shape[0], 2, g["in_features"]))
+    assert fut.shape == g["future"].shape and fut2.shape == g["future_len2"].shape
+    assert rel(past, g["past"]) <= OUT_TOL and rel(losses["feat"], g["feat"]) <= OUT_TOL
+    assert rel(fut, g["future"]) <= 2 * OUT_TOL and rel(fut2, g["future_len2"]) <= 2 * OUT_TOL
+
+
 def test_full_model_matches_reference_golden():
     """BaseModel-level parity through the glue: golden from the unmodified reference BaseModel/TIMMModel/AVTh."""
     from avt_b200.model import AVTModel

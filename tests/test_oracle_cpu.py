@@ -36,6 +36,21 @@ def test_oracle_avth_matches_reference_golden():
             assert rel(p.grad, g["grads"][n]) < 2e-5, n
 
 
+def test_oracle_avth_rollout_matches_reference_golden():
+    """Evaluation rollout (output_len_eval = 3 and a 3-d target_shape) of the oracle vs the UNMODIFIED reference AVTh with
+    the installed HF GPT2Model and its KV cache (oracle/gen_golden.py: gen_avth_rollout)."""
+    g = torch.load(os.path.join(GOLDEN, "avth_rollout_ref_small.pt"))
+    m = o_avth.AVTh(g["in_features"], future_pred_loss="mse", **g["cfg"])
+    m.load_state_dict(g["state"])
+    m.eval()
+    with torch.no_grad():
+        past, fut, losses, _ = m(g["x"], (g["x"].shape[0],))
+        _, fut2, _, _ = m(g["x"], (g["x"].shape[0], 2, g["in_features"]))
+    assert fut.shape == g["future"].shape and fut2.shape == g["future_len2"].shape
+    assert rel(past, g["past"]) < 1e-5 and rel(fut, g["future"]) < 1e-5 and rel(losses["feat"], g["feat"]) < 1e-5
+    assert rel(fut2, g["future_len2"]) < 1e-5
+
+
 def test_oracle_basemodel_matches_reference_golden():
     g = torch.load(os.path.join(GOLDEN, "basemodel_ref_small.pt"))
     m = o_base.BaseModel("vit_test_patch16_32", 64, 32, head_kwargs=g["head"])
