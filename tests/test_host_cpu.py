@@ -153,3 +153,20 @@ def test_bench_reference_arm_schema():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_reads_measured_peaks_in_any_reasonable_schema(tmp_path, monkeypatch):
+    """bench.peaks(): the driver-written MEASURED_PEAKS.json is preferred, the profiling recipe's numbers are the fallback."""
+    import json
+    import bench
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.peaks() == (1400.0, 1590.0, 6650.0, "fallback")
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"bf16_tflops": 1639.1, "bf16_tflops_sustained": 1361.3,
+                                                                "hbm_gbs": 6559.7}))
+    assert bench.peaks() == (1361.3, 1639.1, 6559.7, "measured")
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"peaks": {"dense_bf16_TFLOPs_burst": 1639.1,
+                                                                          "dense_bf16_TFLOPs_sustained": 1361.3,
+                                                                          "HBM_copy_GBs": 6559.7}}))
+    assert bench.peaks() == (1361.3, 1639.1, 6559.7, "measured")
+    (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
+    assert bench.peaks()[3] == "fallback"
