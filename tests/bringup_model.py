@@ -1,5 +1,5 @@
 """GPU bring-up: module-level parity of the drop-in backbone / head against the CPU oracle + step timing.
-Prints relative errors; not a test.   python tools/bringup_model.py [quick|full|time]
+Prints relative errors; a manual checker (lives under tests/ because it uses the oracle).   python tests/bringup_model.py [quick|full|time]
 """
 import os
 import sys
