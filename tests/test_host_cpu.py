@@ -170,3 +170,41 @@ def test_bench_reads_measured_peaks_in_any_reasonable_schema(tmp_path, monkeypat
     assert bench.peaks() == (1361.3, 1639.1, 6559.7, "measured")
     (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
     assert bench.peaks()[3] == "fallback"
+
+
+def test_finish_backward_interleaves_sgd_with_collective_waits():
+    """FlatDataParallel.finish_backward(optimizer): AVT-h buffer first (its all-reduce finished long ago, its update hides
+    the tail of the collective), then the backbone slices, then the torch-owned rest - each update only after ITS waits."""
+    from avt_b200.parallel import FlatDataParallel
+    log = []
+
+    class H:
+        def __init__(self, name):
+            self.name = name
+
+        def wait(self):
+            log.append("wait " + self.name)
+
+    class Opt:
+        def __init__(self, mods):
+            self.mods = mods
+
+        def sync_lr(self):
+            log.append("lr")
+
+        def step_flat(self, i):
+            log.append(f"step_flat {i}")
+
+        def step_other(self):
+            log.append("step_other")
+
+    dp = FlatDataParallel.__new__(FlatDataParallel)
+    dp.group, dp.comm_sms = None, 0
+    dp.vit, dp.head = object(), object()
+    dp.other = []
+    dp._other_handles, dp._other_early = [H("other")], set()
+    dp._head_handles, dp._handles = [H("head")], [H("vit11"), H("vit0"), H("rest")]
+    dp.finish_backward(Opt([dp.vit, dp.head]))
+    assert log == ["lr", "wait head", "step_flat 1", "wait vit11", "wait vit0", "wait rest", "step_flat 0", "wait other",
+                   "step_other"]
+    assert dp._handles == [] and dp._head_handles == [] and dp._other_handles == []
