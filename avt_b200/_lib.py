@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavt_b200.so")
+# AVT_B200_LIB: load another build of the same C-ABI instead (kernel A/B experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("AVT_B200_LIB") or os.path.join(_HERE, "libavt_b200.so")
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
 

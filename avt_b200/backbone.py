@@ -142,28 +142,29 @@ class VisionTransformer(nn.Module):
         assert tuple(x.shape[1:]) == (self.in_chans, self.img_size, self.img_size), x.shape
         pk.refresh_bf16()
         w = st.workspace(M, F, ntok, train)
-        key = ("patch", M)
-        if key not in self._aux:
-            self._aux[key] = torch.empty(M, Kp, dtype=torch.bfloat16, device=x.device)
-            self._aux[("fstat", F)] = torch.empty(2, F, dtype=torch.float32, device=x.device)
-            self._aux[("xcls", F)] = torch.empty(F, D, dtype=torch.float32, device=x.device)
+        if w["aux"] is None:   # buffers the backward reads: they belong to the workspace, not to the module
+            w["aux"] = dict(patch=torch.empty(M, Kp, dtype=torch.bfloat16, device=x.device),
+                            fstat=torch.empty(2, F, dtype=torch.float32, device=x.device),
+                            xcls=torch.empty(F, D, dtype=torch.float32, device=x.device))
+        if ("fsum", ntok) not in self._aux:   # scratch of one kernel call
             self._aux[("fsum", ntok)] = torch.empty(ntok * D, dtype=torch.float32, device=x.device)
-        A = self._aux[key]
+        A = w["aux"]["patch"]
         ops.patchify(x, A, self.patch_size)
         ops.gemm(A, pk.bv("patch_embed.proj.weight").view(D, Kp), w["x"][0], bias=pk.wv("patch_embed.proj.bias"),
                  pos=pk.wv("pos_embed").view(ntok, D), cls=pk.wv("cls_token").view(D), pos_period=ntok)
         xmid, y = st.forward(w, F, ntok, train)
         feats = torch.empty(F, D, dtype=torch.float32, device=x.device)
-        fst = self._aux[("fstat", F)]
-        xcls = self._aux[("xcls", F)]
+        fst, xcls = w["aux"]["fstat"], w["aux"]["xcls"]
         # final residual add + LayerNorm on the CLS rows only (timm: norm(x)[:, 0]; the other 196 rows are dead)
         ops.layernorm_fwd(xmid, pk.wv("norm.weight"), pk.wv("norm.bias"), 1e-6, feats, fst[0], fst[1], rows=F,
                           x_stride=ntok * D, add=y, add_stride=ntok * D, x_out=xcls)
-        return feats, (w, xcls, F)
+        return feats, (w, st.lease(w) if train else None, F)
 
     def _run_backward(self, saved, dfeats):
         pk, st = self._pack, self._stack
-        w, xcls, F = saved
+        w, lease, F = saved
+        st.check_lease(w, lease)
+        xcls = w["aux"]["xcls"]
         ntok, D = self.num_tokens, self.embed_dim
         M = F * ntok
         Kp = self.in_chans * self.patch_size ** 2
@@ -172,17 +173,18 @@ class VisionTransformer(nn.Module):
         dx, dxb = w["dx"], w["dxb"]
         dx.zero_()
         dxb.zero_()
-        fst = self._aux[("fstat", F)]
+        fst = w["aux"]["fstat"]
         # only the CLS rows of dx are non-zero here, so their column sums are the last fc2's bias gradient
         ops.layernorm_bwd(dfeats, xcls, fst[0], fst[1], pk.wv("norm.weight"), dx, pk.gv("norm.weight"), pk.gv("norm.bias"),
                           w["lnws"], dx_bf16=dxb, rows=F, dx_stride=ntok * D, dxb_stride=ntok * D,
                           dx_colsum=pk.gv(f"blocks.{len(self.blocks) - 1}.mlp.fc2.bias"))
         st.backward(w, dx, dxb, top_bias_done=True)
-        A = self._aux[("patch", M)]
+        A = w["aux"]["patch"]
         sk = engine._split_k_for(D, Kp, M, 256)
         ops.gemm(dxb, A, pk.gv("patch_embed.proj.weight").view(D, Kp), a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1)
         ops.frame_sum_grads(dx, F, ntok, D, self._aux[("fsum", ntok)], dpos=pk.gv("pos_embed"), dcls=pk.gv("cls_token"),
                             dbias=pk.gv("patch_embed.proj.bias"), accumulate=False)
+        lease.done = True
         if self._grads_ready_hook is not None:
             self._grads_ready_hook()
 

@@ -745,6 +745,32 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
   return AVT_OK;
 }
 
+// 3-D tensor map over a row-major bf16 matrix viewed as [outer2][outer1][inner] (e.g. [frame][token][column]): boxes never
+// cross an outer2 boundary - rows past `outer1` are out of bounds, so loads zero-fill them and stores drop them.
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer1, uint64_t outer2, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer1, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled", "driver entry point not available", __FILE__, __LINE__);
+    return AVT_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {inner, outer1, outer2};
+  cuuint64_t strides[2] = {ld * 2, ld * 2 * outer1};
+  cuuint32_t box[3] = {box_inner, box_outer1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "CUresult %d (3-D, base %p inner %llu outer %llu x %llu ld %llu)", (int)r, base,
+             (unsigned long long)inner, (unsigned long long)outer1, (unsigned long long)outer2, (unsigned long long)ld);
+    set_last_error("cuTensorMapEncodeTiled", msg, __FILE__, __LINE__);
+    return AVT_ERR_CUDA;
+  }
+  return AVT_OK;
+}
+
 struct GemmMaps {
   CUtensorMap a, b, out, aux, in;
 };

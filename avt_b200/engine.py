@@ -11,6 +11,7 @@ torch is used here only to own device memory and streams; every arithmetic step 
 C-ABI. No autograd, no torch math.
 """
 import math
+import weakref
 from dataclasses import dataclass
 
 import torch
@@ -28,19 +29,24 @@ class ParamPack:
         # vectors (biases, LayerNorm) first: their gradients are produced by atomics and need zero-initialisation
         # each backward; matrices follow in module order (one layer's matrices are contiguous, so a layer's weight
         # gradients can be all-reduced as one slice while the backward of earlier layers is still running).
+        # Within the vectors the biases come first: the reference puts every parameter whose name ends in 'bias' into its
+        # own optimizer group with weight decay x opt.bias_bn_wd_scale (func/train.py:704-731), so [0, bias_end) and
+        # [bias_end, total) are the two weight-decay regions of the fused SGD.
         small = [(n, p) for n, p in named_params if p.dim() < 2]
+        small = [(n, p) for n, p in small if n.endswith("bias")] + [(n, p) for n, p in small if not n.endswith("bias")]
         big = [(n, p) for n, p in named_params if p.dim() >= 2]
         self.names, self.slices, self.shapes = [], {}, {}
         off = 0
+        self.bias_end = self.small_end = 0
         for n, p in small + big:
             self.names.append(n)
             self.slices[n] = (off, p.numel())
             self.shapes[n] = tuple(p.shape)
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
-            if n == (small[-1][0] if small else None):
+            if p.dim() < 2:
                 self.small_end = off
-        if not small:
-            self.small_end = 0
+                if n.endswith("bias"):
+                    self.bias_end = off
         self.total = off
         self.device = device
         self.w = torch.zeros(off, dtype=torch.float32, device=device)
@@ -75,7 +81,9 @@ class ParamPack:
         return all(p.data_ptr() == self._ptrs[n] and p.device == self.w.device for n, p in self.params.items())
 
     def _signature(self):
-        return sum(p._version for p in self.params.values())
+        # in-place writes to the flat buffer itself (a stock optimizer stepping on flat_parameter_groups(), a broadcast)
+        # bump only w._version, writes through the parameter views only the parameters'
+        return self.w._version + sum(p._version for p in self.params.values())
 
     def refresh_bf16(self):
         """Down-cast the master weights unless nothing touched them since the shadow was last written (torch
@@ -167,7 +175,16 @@ def _split_k_for(m_w, n_w, k_rows, block_n, sms=148):
     return _best_split(tiles, kblocks, sms // 2, min(32, kblocks // 8), 8)
 
 
+class Lease:
+    """Ownership of one activation workspace by the forward whose backward still has to read it. Lives on that forward's
+    autograd ctx: the workspace is handed out again once the backward has run (`done`) or the graph was dropped (the
+    weak reference died). `gen` detects a backward over activations a later forward has overwritten."""
+    __slots__ = ("gen", "done", "__weakref__")
+
+
 class BlockStack:
+    MAX_LIVE_WORKSPACES = 8   # forwards of one shape whose backward is still pending (multi-crop, gradient accumulation)
+
     def __init__(self, spec: StackSpec, pack: ParamPack):
         self.s, self.pack = spec, pack
         self.ws = {}
@@ -215,9 +232,33 @@ class BlockStack:
     # ------------------------------------------------------------------ workspace
     def _workspace(self, M, nb, ntok, train):
         key = (M, nb, ntok, train)
-        w = self.ws.get(key)
-        if w is not None:
-            return w
+        pool = self.ws.setdefault(key, [])
+        for w in pool:
+            lease = w["lease"]() if w["lease"] is not None else None
+            if lease is None or lease.done:
+                return w
+        if len(pool) >= self.MAX_LIVE_WORKSPACES:
+            raise RuntimeError(f"{len(pool)} forwards of shape {key} are waiting for their backward: every one of them keeps "
+                               "a full set of activations alive (run backward, or drop the graphs, before the next forward)")
+        w = self._alloc_workspace(M, nb, ntok, train)
+        pool.append(w)
+        return w
+
+    def lease(self, w):
+        """Mark `w` as owned by the forward that just filled it (train mode); keep the returned object on the autograd ctx."""
+        lease = Lease()
+        w["gen"] += 1
+        lease.gen, lease.done = w["gen"], False
+        w["lease"] = weakref.ref(lease)
+        return lease
+
+    @staticmethod
+    def check_lease(w, lease):
+        if lease.gen != w["gen"]:
+            raise RuntimeError("the activations saved by this forward were overwritten by a later forward of the same shape "
+                               "(backward called twice with retain_graph after another forward ran)")
+
+    def _alloc_workspace(self, M, nb, ntok, train):
         s, dev = self.s, self.pack.device
         D, L = s.dim, s.layers
         bf, f32 = torch.bfloat16, torch.float32
@@ -236,7 +277,7 @@ class BlockStack:
             w.update({"dx": e(M, D, dt=f32), "dxb": e(M, D), "dz": e(M, 4 * D), "dln": e(M, D), "datt": e(M, D),
                       "dqkv": e(M, 3 * D), "g": e(M, D),
                       "lnws": torch.empty(ops.layernorm_bwd_workspace(M, D), dtype=torch.uint8, device=dev)})
-        self.ws[key] = w
+        w.update({"lease": None, "gen": 0, "aux": None})   # aux: the owning module's own per-forward buffers
         return w
 
     # ------------------------------------------------------------------ forward

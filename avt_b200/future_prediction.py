@@ -178,9 +178,8 @@ class AVTh(nn.Module):
         drop = self.training  # nn.Dropout semantics: active in train() mode only
         pk.refresh_bf16()
         w = st.workspace(M, B, T, train_graph)
-        key = ("io", M)
-        if key not in self._aux:
-            self._aux[key] = dict(xb=torch.empty(M, C, dtype=torch.bfloat16, device=dev),
+        if w["aux"] is None:   # buffers the backward reads: they belong to the workspace, not to the module
+            w["aux"] = dict(xb=torch.empty(M, C, dtype=torch.bfloat16, device=dev),
                                   lnf=torch.empty(M, Dh, dtype=torch.bfloat16, device=dev),
                                   fst=torch.empty(2, M, dtype=torch.float32, device=dev),
                                   db=torch.empty(M, C, dtype=torch.bfloat16, device=dev),
@@ -188,7 +187,7 @@ class AVTh(nn.Module):
                                   g32=torch.empty(M, Dh, dtype=torch.float32, device=dev),
                                   gb=torch.empty(M, Dh, dtype=torch.bfloat16, device=dev),
                                   fsum=torch.empty(T * Dh, dtype=torch.float32, device=dev))
-        a = self._aux[key]
+        a = w["aux"]
         # Philox stream: seed from torch's global seed; the per-step offset lives in DEVICE memory and is advanced by a
         # (capturable) in-place add, so a CUDA-graph replay of the step draws fresh dropout masks. Each forward keeps
         # its own snapshot for its backward.
@@ -213,13 +212,14 @@ class AVTh(nn.Module):
         decoded = torch.empty(M, C, dtype=torch.float32, device=dev)
         sk = engine.small_m_split(M, C, Dh)
         ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded, split_k=sk, workspace=st._gemm_ws(decoded, sk))
-        return decoded, (w, xf, B, T, p_embd, seed, off, off_dev)
+        return decoded, (w, st.lease(w) if train_graph else None, xf, B, T, p_embd, seed, off, off_dev)
 
     def _run_backward(self, saved, ddec):
         pk, st = self._pack, self._stack
-        w, xf, B, T, p_embd, seed, off, off_dev = saved
+        w, lease, xf, B, T, p_embd, seed, off, off_dev = saved
+        st.check_lease(w, lease)
         M, C, Dh = B * T, self.in_features, self.inter_dim
-        a = self._aux[("io", M)]
+        a = w["aux"]
         pk.zero_small_grads()
         ops.cast_bf16(ddec.contiguous().float(), a["db"])
         ops.gemm(a["db"], a["lnf"], pk.gv("decoder.weight"), a_mn=True, b_mn=True)          # dWdec = ddec^T lnf
@@ -240,6 +240,7 @@ class AVTh(nn.Module):
         sk = engine.small_m_split(M, C, Dh)
         ops.gemm(gb, pk.bv("encoder.weight"), dfeats, b_mn=True, split_k=sk,                 # dfeats = g Wenc
                  workspace=st._gemm_ws(dfeats, sk))
+        lease.done = True
         if self._grads_ready_hook is not None:
             self._grads_ready_hook()
         return dfeats

@@ -66,3 +66,16 @@ def training_loss(outputs, aux_losses, target, target_subclips=None, past_tgt=No
                                                 reduction="none").view(past_tgt.shape)
     losses.update(aux_losses)
     return sum(torch.mean(v) for v in losses.values())
+
+
+def accuracy(output, target, topk=(1,)):
+    """Top-k accuracies in percent, as `common/utils.py:17-44` computes them every training iteration
+    (func/train_eval_ops.py:61-63). The reference's early-out `if torch.all(target < 0)` is a device synchronisation; it
+    returns zeros, which is also what the general formula gives (a negative label never equals a predicted class), so the
+    branch is dropped and the step stays capturable in a CUDA graph."""
+    with torch.no_grad():
+        output = output.flatten(0, -2)
+        target = target.flatten()
+        _, pred = output.topk(max(topk), 1, True, True)
+        correct = pred.t().eq(target[None])
+        return [correct[:k].flatten().sum(dtype=torch.float32) * (100.0 / target.size(0)) for k in topk]

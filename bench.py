@@ -110,10 +110,23 @@ def synth_batch(torch, B, T, rank, device, pin=False):
 
 
 # ----------------------------------------------------------------------------------------- CPU reference arm
+def use_all_host_cores(torch):
+    """torchrun exports OMP_NUM_THREADS=1 to every worker; the CPU legs are a whole-host baseline, so give them every
+    core the process may run on (round-1 N >= 2 reference lines were timed on ONE thread)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def cpu_reference_step_time(torch, model_type, T, steps, warmup, batch=1):
     """The reference's own path on host cores: oracle port of BaseModel + timm ViT + AVTh (HF GPT-2 math), fp32,
     train() mode with the reference's dropout defaults, fwd + loss + bwd."""
     from oracle import base_model as ob
+    use_all_host_cores(torch)
     torch.manual_seed(42)
     dim = 1024 if "large" in model_type else 768
     m = ob.BaseModel(model_type, dim, NUM_CLASSES)
@@ -137,15 +150,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
-    times = cpu_reference_step_time(torch, args.model, args.frames, args.steps, max(1, min(args.warmup, 1)), batch=1)
+    cores = use_all_host_cores(torch)
+    warm = max(1, args.warmup)                      # every requested warm-up step is run (a CPU step is ~0.5 s)
+    times = cpu_reference_step_time(torch, args.model, args.frames, args.steps, warm, batch=1)
     per = sum(times) / len(times)
     v = 1.0 / per
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"AVT-b {args.model} + AVT-h (expts/01), T={args.frames}, 224x224, fwd+loss+bwd on CPU",
-                       "sample": "1 clip per step"},
+            "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
                              "sample": f"oracle port of the reference path, 1 clip x {args.frames} frames per step, {len(times)} steps"},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -158,7 +171,7 @@ def run_ours(args):
     import torch.distributed as dist
     from avt_b200 import _lib, ops
     from avt_b200.graph import GraphedStep
-    from avt_b200.model import AVTModel, past_targets, training_loss
+    from avt_b200.model import AVTModel, accuracy, past_targets, training_loss
     from avt_b200.optim import FlatSGD
     from avt_b200.parallel import FlatDataParallel
 
@@ -189,12 +202,12 @@ def run_ours(args):
         """forward -> loss -> backward -> gradient all-reduce -> optimizer step (func/train.py:204-233)"""
         out, aux = model(video, target_shape=(B,))
         loss = training_loss(out, aux, target, past_tgt=past_tgt)
+        state["acc"] = accuracy(out["logits/action"], target, topk=(1, 5))   # train_eval_ops.py:61-63, every iteration
         if state["opt"] is None:                                     # flat buffers exist after the first forward
             dp.broadcast_parameters()
             state["opt"] = FlatSGD([dp.vit, dp.head], dp.other, lr=1e-4 * world, momentum=0.9, nesterov=True,
                                    weight_decay=1e-6)                 # expts/01:26-28, func/train.py:718
-        for p in dp.other:
-            p.grad = None
+        state["opt"].zero_grad()                                     # func/train.py:221
         loss.backward()
         dp.finish_backward(state["opt"])     # waits for the collectives piecewise and applies the fused SGD in between
         return loss
@@ -328,8 +341,12 @@ def run_ours(args):
 
     ops.attention_tc_fwd, ops.attention_tc_bwd = timed_call(orig_af), timed_call(orig_ab)
     ops.gemm = timed_gemm
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
     core(video_d, target_d, past_targets(sub_d))                     # eager, so that the events bracket each launch
+    ee1.record()
     torch.cuda.synchronize()
+    eager_ms = ee0.elapsed_time(ee1)
     ops.gemm = orig
     ops.attention_tc_fwd, ops.attention_tc_bwd = orig_af, orig_ab
     attn_ms = sum(a.elapsed_time(b) for a, b in attn_events)
@@ -342,29 +359,38 @@ def run_ours(args):
     gflop_clip = GFLOP_PER_CLIP.get((args.model, T))
     step_tf = (gflop_clip * 1e9 * B / (ms_per_step * 1e-3) / 1e12) if gflop_clip else None
 
+    # DRAM bytes per ViT GEMM launch: not measurable inside this process (needs ncu); taken from the committed ncu launch
+    # list of this same command (tools/summarize_profiles.py writes the JSON), null when that file is absent
+    traffic, traffic_src = None, "no ncu summary for this workload under profiles/"
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as fh:
+            tj = json.load(fh).get(f"{args.model}:{T}:{B}")
+        if tj:
+            traffic, traffic_src = tj["bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"AVT-b {args.model} + AVT-h (expts/01: inter_dim 2048, 6 layers, 4 heads), T={T}, 224x224, "
-                                   f"{B} clips/GPU, fwd+loss+bwd+allreduce+SGD step", "clips_per_gpu": B, "frames": T,
-                       "parallelism": f"dp{world}", "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2",
-                       "init": "reference init (nn.Linear N(0,0.01)), seed 42", "dropout": "reference defaults (0.1 GPT-2, 0.2 model)",
-                       "launch": runner["note"],
-                       "e2e_input": "pinned host batch -> device staging buffer on a copy stream, overlapped with the previous "
-                                    "step (double-buffered prefetch); one H2D copy per step inside the timed region"},
+            "config": workload_config(args, world),
+            "notes": {"l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2", "launch": runner["note"],
+                      "e2e_input": "pinned host batch -> device staging buffer on a copy stream, overlapped with the previous "
+                                   "step (double-buffered prefetch); one H2D copy per step inside the timed region",
+                      "roofline_timing": f"per-kernel CUDA events of ONE eager instrumented step ({eager_ms:.2f} ms eager vs "
+                                         f"{ms_per_step:.2f} ms for the graph replay the headline value times; the kernels are "
+                                         "the same launches, the graph only removes host enqueue gaps)"},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus,
-                         "traffic": 115.4e6, "kernel": "gemm_bf16_kernel (tcgen05), ViT GEMMs (M = 15 760 rows)",
+                         "traffic": traffic, "kernel": "gemm_bf16_kernel (tcgen05), ViT GEMMs (M = 15 760 rows)",
                          "peak_source": f"{src} bf16_tflops_sustained",
                          "how": "sum of 2*M*N*K over the ViT GEMM launches of one step / sum of their CUDA-event durations",
-                         "traffic_source": "profiles/r01_step_launches.md: ncu dram__bytes_read+write, mean per launch of the "
-                                           "146 ViT GEMM launches of one step (algorithmic operand+output bytes: 117.6 MB)",
+                         "traffic_source": traffic_src,
                          "launches": len(vit_events), "gemm_ms_per_step": gemm_ms, "step_achieved": step_tf,
                          "step_frac": (step_tf / sus) if step_tf else None},
             "attention": {"achieved": attn_tf, "unit": "TFLOP/s", "peak": sus, "frac": attn_tf / sus, "ms_per_step": attn_ms,
@@ -379,7 +405,7 @@ def run_ours(args):
                                      "(eager launches: includes ~10 us of launch/ramp per call)"},
         }
         if args.cpu_baseline:
-            cores = torch.get_num_threads()
+            cores = use_all_host_cores(torch)
             times = cpu_reference_step_time(torch, args.model, T, 2, 1, batch=1)
             per = sum(times) / len(times)
             line["cpu_baseline"] = {"value": 1.0 / per, "unit": "clips/s", "cores": cores, "kind": "port",
@@ -396,15 +422,31 @@ def run_ours(args):
         os._exit(0)
 
 
+CONFIGS = {   # BASELINE.json `configs` (index in the list) -> (model_type, frames, clips per GPU)
+    "cfg2": ("vit_base_patch16_224", 10, 8),    # [1] / [2]: expts/01_ek100_avt, 8 clips per GPU (global 64 on 8 GPUs)
+    "cfg4": ("vit_base_patch16_224", 15, 8),    # [3]: expts/07_ek100_avt_longer (T = 15)
+    "cfg5": ("vit_large_patch16_224", 10, 8),   # [4]: ViT-L/16 stress
+}
+
+
+def workload_config(args, world):
+    """`config` of the JSON line: the same dict for both arms (the CPU arm times a bounded sample of this workload)."""
+    return {"workload": f"{args.config}: AVT-b {args.model} + AVT-h (expts/01: inter_dim 2048, 6 layers, 4 heads), T={args.frames}, "
+                        f"224x224, {args.batch} clips/GPU, fwd+loss+bwd+allreduce+SGD step",
+            "clips_per_gpu": args.batch, "frames": args.frames, "parallelism": f"dp{world}",
+            "init": "reference init (nn.Linear N(0,0.01)), seed 42", "dropout": "reference defaults (0.1 GPT-2, 0.2 model)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="clips per GPU")
-    ap.add_argument("--frames", type=int, default=10)
-    ap.add_argument("--model", default="vit_base_patch16_224")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json workload preset")
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default: the preset's)")
+    ap.add_argument("--frames", type=int, default=None, help="frames per clip (default: the preset's)")
+    ap.add_argument("--model", default=None, help="timm model_type (default: the preset's)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python each step")
     ap.add_argument("--comm-sms", type=int, default=0,
@@ -412,6 +454,10 @@ def main():
                          "on 8 GPUs the 1.58 GB fp32 all-reduce did not fit under the backward with 16 channels; 124 SMs keep "
                          "the forward / dgrad GEMMs at the same 12 / 9 / 3 tile rounds as 132)")
     args = ap.parse_args()
+    model, frames, batch = CONFIGS[args.config]
+    args.model = args.model or model
+    args.frames = args.frames or frames
+    args.batch = args.batch or batch
     if args.impl == "reference":
         run_reference(args)
     else:
