@@ -36,7 +36,25 @@ class AVTModel(nn.Module):
                     nn.init.constant_(m.bias, 0)
 
     def forward(self, video, target_shape=None):
-        """video (B, #clips=T, C, T'=1, H, W) -> (outputs dict, aux_losses dict)."""
+        """video (B, #clips, C, T', H, W) or (B, #clips, #crops, C, T', H, W) -> (outputs, aux_losses), each averaged over
+        the crops: the test-time-augmentation loop of models/base_model.py:239-273 (3 crops x flip at evaluation,
+        common/transforms.py:254-296). Every crop is one full forward; in train mode each keeps its own activation workspace
+        until the backward (engine.Lease)."""
+        if video.ndim == 6:
+            crops = [video]
+        elif video.ndim == 7 and video.size(2) == 1:
+            crops = [video.squeeze(2)]
+        elif video.ndim == 7:
+            crops = torch.unbind(video, dim=2)
+        else:
+            raise NotImplementedError("Unsupported size %s" % (video.shape,))
+        feats, losses = zip(*[self.forward_singlecrop(c, target_shape) for c in crops])
+        feats = {k: torch.mean(torch.stack([d[k] for d in feats], dim=0), dim=0) for k in feats[0]}
+        losses = {k: torch.mean(torch.stack([d[k] for d in losses], dim=0), dim=0) for k in losses[0]}
+        return feats, losses
+
+    def forward_singlecrop(self, video, target_shape=None):
+        """video (B, #clips=T, C, T'=1, H, W) -> (outputs dict, aux_losses dict)  [models/base_model.py:140-220]"""
         B, num_clips = video.size(0), video.size(1)
         feats = self.backbone(video.flatten(0, 1))                      # base_model.py:153-154
         feats = torch.mean(feats, [-1, -2]).permute((0, 2, 1))          # :157, :166

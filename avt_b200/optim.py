@@ -60,5 +60,13 @@ class FlatSGD:
             self.other.step()
 
     def zero_grad(self, set_to_none=True):
+        """optimizer.zero_grad() of the reference loop (func/train.py:221). The flat modules overwrite their gradient
+        buffers every backward; the torch-owned parameters accumulate like any autograd leaf, so ALL of them are cleared
+        here - also the big ones that step through the fused kernel and are not in the inner torch optimizer."""
+        for p in self.fused_other:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
         if self.other is not None:
             self.other.zero_grad(set_to_none=set_to_none)

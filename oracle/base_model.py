@@ -49,7 +49,21 @@ class BaseModel(nn.Module):
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
 
-    def forward(self, video, target_shape=None):
+    def forward(self, video, target_shape=None):   # models/base_model.py:239-273 (crops averaged)
+        if video.ndim == 6:
+            crops = [video]
+        elif video.ndim == 7 and video.size(2) == 1:
+            crops = [video.squeeze(2)]
+        elif video.ndim == 7:
+            crops = torch.unbind(video, dim=2)
+        else:
+            raise NotImplementedError("Unsupported size %s" % (video.shape,))
+        feats, losses = zip(*[self.forward_singlecrop(c, target_shape) for c in crops])
+        feats = {k: torch.mean(torch.stack([d[k] for d in feats], dim=0), dim=0) for k in feats[0]}
+        losses = {k: torch.mean(torch.stack([d[k] for d in losses], dim=0), dim=0) for k in losses[0]}
+        return feats, losses
+
+    def forward_singlecrop(self, video, target_shape=None):
         B, num_clips = video.size(0), video.size(1)
         feats = self.backbone(video.flatten(0, 1))                 # :153-154   (B*T, C, 1, 1, 1)
         feats = torch.mean(feats, [-1, -2]).permute((0, 2, 1))     # :157,166   (B*T, 1, C)

@@ -208,3 +208,49 @@ def test_finish_backward_interleaves_sgd_with_collective_waits():
     assert log == ["lr", "wait head", "step_flat 1", "wait vit11", "wait vit0", "wait rest", "step_flat 0", "wait other",
                    "step_other"]
     assert dp._handles == [] and dp._head_handles == [] and dp._other_handles == []
+
+
+def test_reference_basemodel_hosts_the_dropins():
+    """The drop-in boundary against the REAL glue: the unmodified reference `models.base_model.BaseModel`
+    (models/base_model.py:22-26,65-68) instantiates avt_b200's backbone / head through their Hydra `_target_` paths, ends up
+    with the same parameter names and shapes as with its own modules, `_initialize_weights` (:110-127) gives the same
+    init statistics, and `init_from_model`-style loading (func/train.py:679-688) works. Needs /root/reference (authoring
+    container only); the GPU box skips it."""
+    from oracle import ref_host
+    if not ref_host.available():
+        pytest.skip("reference checkout not present")
+    ref_host.install_stubs()
+    from models.base_model import BaseModel
+    head = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32)
+    torch.manual_seed(0)
+    cfg_ref = ref_host.model_cfg("vit_test_patch16_32", 64, head=head)
+    ref = BaseModel(cfg_ref, {"action": 37}, {})
+    torch.manual_seed(0)
+    cfg = ref_host.model_cfg("vit_test_patch16_32", 64, head=head)
+    cfg["backbone"] = {"_target_": "avt_b200.backbone.TIMMModel", "model_type": "vit_test_patch16_32"}
+    cfg["future_predictor"] = dict(cfg["future_predictor"], _target_="avt_b200.future_prediction.AVTh")
+    ours = BaseModel(cfg, {"action": 37}, {})
+    from avt_b200.backbone import TIMMModel
+    from avt_b200.future_prediction import AVTh
+    assert isinstance(ours.backbone, TIMMModel) and isinstance(ours.future_predictor, AVTh)
+    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
+    assert a == b, set(a) ^ set(b)
+    assert sum(p.numel() for p in ours.parameters()) == sum(p.numel() for p in ref.parameters())
+    # BaseModel._initialize_weights re-initialises nn.Linear children: same statistics on both sides
+    for name in ("backbone.model.blocks.0.attn.qkv.weight", "future_predictor.encoder.weight", "classifiers.action.weight"):
+        so, sr = dict(ours.named_parameters())[name].std().item(), dict(ref.named_parameters())[name].std().item()
+        assert abs(so - sr) < 0.15 * sr and abs(sr - 0.01) < 2e-3, (name, so, sr)
+    so = ours.future_predictor.gpt_model.h[0].attn.c_attn.weight.std().item()      # HF Conv1D: untouched, N(0, 0.02)
+    assert abs(so - 0.02) < 4e-3
+    # train.init_from_model=[[backbone.model, ckpt]] -> attrgetter('backbone.model')(model).load_state_dict(sd, strict=False)
+    import operator
+    sd = {k: torch.randn_like(v) for k, v in ref.backbone.model.state_dict().items()}
+    res = operator.attrgetter("backbone.model")(ours).load_state_dict(sd, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(ours.backbone.model.blocks[1].mlp.fc1.weight, sd["blocks.1.mlp.fc1.weight"])
+    # whole-model strict resume from a reference checkpoint (func/train.py:764)
+    ours.load_state_dict({k: v for k, v in ref.state_dict().items()}, strict=True)
+    # no CPU path: the reference glue reaches our backbone and gets the loud error, not a silent fallback
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ours(torch.zeros(1, 2, 3, 1, 32, 32), target_shape=(1,))

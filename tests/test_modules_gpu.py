@@ -3,11 +3,14 @@
 Tolerance policy (stated once, used below). The north star asks for 1e-3 relative on the bf16 path; that bound is
 met at kernel level on identically-rounded operands (tests/test_gemm_gpu.py, test_kernels_gpu.py). At module level
 every GEMM operand is *stored* in bf16 (2^-9 relative rounding each), so an L-layer stack cannot be closer than a few
-1e-3 to an fp64 oracle — torch's own bf16 autocast of the oracle lands at 5e-3..9e-3 on these configs. The module
-tests therefore require rel-L2 <= 2e-2 for outputs and <= 4e-2 for parameter gradients against the fp64/fp32 oracle,
-AND that our error does not exceed 1.25x the error of torch-autocast-bf16 on the same inputs (we are consistently
-below it because the residual stream, LayerNorm statistics and softmax stay in fp32).
+1e-3 to an fp64 oracle - torch's own bf16 autocast of the oracle lands at 5e-3..1e-2 on these configs. The module tests
+therefore require, per configuration, (a) rel-L2 <= 1.5x the error this path was MEASURED to have on B200 (table below),
+for outputs and for the worst parameter gradient, AND (b) that neither exceeds 1.25x the error of torch-autocast-bf16 of
+the oracle on the same inputs (we are consistently below it: the residual stream, LayerNorm statistics and softmax stay
+in fp32). A kernel regression that raises an error by 50 % fails.
 """
+import copy
+import json
 import os
 
 import pytest
@@ -19,7 +22,31 @@ from oracle import vit as o_vit
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# Loose bounds for the few comparisons without a recorded error (2x the worst recorded one) ...
 OUT_TOL, GRAD_TOL = 2e-2, 4e-2
+# ... and per configuration (output, worst parameter gradient) rel-L2 bounds = 1.5x the errors measured on B200
+# (tests record them in gpurun_out/parity_errors.json; round 2: outputs 5.0e-3..9.2e-3, gradients 7.0e-3..1.5e-2, always
+# below torch's own bf16 autocast of the oracle on the same inputs, which every test also requires).
+GOLDEN_AVTH_TOL, GOLDEN_BASE_TOL = (9e-3, 1.3e-2), (1.5e-2, 2.9e-2)
+AVTH_TOL = {(64, 32, 5): (9.1e-3, 2.3e-2), (64, 128, 10): (8.7e-3, 1.55e-2), (2048, 768, 10): (8.9e-3, 1.55e-2),
+            (768, 2048, 10): (9.9e-3, 1.5e-2), (768, 2048, 15): (7.8e-3, 1.35e-2)}
+BACKBONE_TOL = {("vit_test_patch16_32", "stress"): (1.05e-2, 1.9e-2), ("vit_test_patch16_64", "stress"): (1.4e-2, 2.2e-2),
+                ("vit_test_patch16_64", "default"): (7.5e-3, 1.05e-2), ("vit_base_patch16_224", "stress"): (9.6e-3, 2.1e-2),
+                ("vit_large_patch16_224", "stress"): (9.2e-3, 2.0e-2)}
+
+
+def record(name, value):
+    """Measured errors -> gpurun_out/parity_errors.json (when the directory exists): the tolerances are kept at <= 1.5x these."""
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    path = os.path.join(d, "parity_errors.json")
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[name] = value
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
 
 
 def rel(a, b):
@@ -63,18 +90,27 @@ def test_backbone_forward_backward_vs_oracle(model_type, F, init, dtype):
     img = o_vit.CONFIGS[model_type][0]
     x = torch.randn(F, 3, img, img, generator=torch.Generator().manual_seed(1))
     gy = torch.randn(F, ref.embed_dim, generator=torch.Generator().manual_seed(2))
+    # what stock PyTorch gives for the same module under bf16 autocast (forward AND gradients): the yardstick
+    auto = copy.deepcopy(ref).cuda()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        ya = ref.cuda()(x.cuda()).float().cpu()
+        ya = auto(x.cuda()).float()
+    ya.backward(gy.cuda())
     ref = ref.cpu().to(dtype)
     yr = ref(x.to(dtype))
     yr.backward(gy.to(dtype))
     yo = ours(x.cuda())
     yo.backward(gy.cuda())
     e_ours, e_autocast = rel(yo, yr), rel(ya, yr)
-    assert e_ours <= OUT_TOL and e_ours <= 1.25 * e_autocast + 1e-4, (e_ours, e_autocast)
-    gr = dict(ref.named_parameters())
-    for n, p in ours.named_parameters():
-        assert p.grad is not None and rel(p.grad, gr[n].grad) <= GRAD_TOL, (n, rel(p.grad, gr[n].grad))
+    gr, ga = dict(ref.named_parameters()), dict(auto.named_parameters())
+    g_ours = {n: rel(p.grad, gr[n].grad) for n, p in ours.named_parameters()}
+    g_auto = {n: rel(ga[n].grad, gr[n].grad) for n in g_ours}
+    worst = max(g_ours, key=g_ours.get)
+    record(f"backbone/{model_type}/{init}", dict(fwd=e_ours, fwd_autocast=e_autocast, grad=g_ours[worst], grad_name=worst,
+                                                grad_autocast=max(g_auto.values())))
+    out_tol, grad_tol = BACKBONE_TOL[(model_type, init)]
+    assert e_ours <= out_tol and e_ours <= 1.25 * e_autocast + 1e-4, (e_ours, e_autocast)
+    assert all(p.grad is not None for p in ours.parameters())
+    assert g_ours[worst] <= grad_tol and g_ours[worst] <= 1.25 * max(g_auto.values()) + 1e-4, (worst, g_ours[worst], max(g_auto.values()))
 
 
 def test_backbone_timm_wrapper_contract_and_no_grad_path():
@@ -137,15 +173,28 @@ def test_avth_forward_backward_vs_oracle(C, Dh, nh, nl, B, T, dtype):
     po, fo, lo, _ = ours(xo, (B,))
     ((po * g1.cuda()).sum() + (fo * g2.cuda()).sum() + lo["feat"].mean()).backward()
     assert po.shape == (B, T, C) and fo.shape == (B, C) and lo["feat"].shape == (B, T - 1, C)
-    assert rel(po, pr) <= OUT_TOL and rel(fo, fr) <= OUT_TOL and rel(lo["feat"], lr["feat"]) <= OUT_TOL
-    assert rel(xo.grad, xr.grad) <= GRAD_TOL
-    gr = dict(ref.named_parameters())
+    # stock PyTorch bf16 autocast of the same module on the same inputs: the yardstick
+    auto = copy.deepcopy(ref).float().cuda()
+    xa = x.clone().cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pa, fa, la, _ = auto(xa, (B,))
+        ((pa.float() * g1.cuda()).sum() + (fa.float() * g2.cuda()).sum() + la["feat"].float().mean()).backward()
+    e_out = max(rel(po, pr), rel(fo, fr), rel(lo["feat"], lr["feat"]))
+    a_out = max(rel(pa, pr), rel(fa, fr), rel(la["feat"], lr["feat"]))
+    gr, ga = dict(ref.named_parameters()), dict(auto.named_parameters())
+    g_ours, g_auto = {"x": rel(xo.grad, xr.grad)}, {"x": rel(xa.grad, xr.grad)}
     for n, p in ours.named_parameters():
         if n == "gpt_model.wpe.weight":
             assert torch.count_nonzero(p.grad[T:]) == 0      # only positions 0..T-1 are used
-            assert rel(p.grad[:T], gr[n].grad[:T]) <= GRAD_TOL
+            g_ours[n], g_auto[n] = rel(p.grad[:T], gr[n].grad[:T]), rel(ga[n].grad[:T], gr[n].grad[:T])
         else:
-            assert rel(p.grad, gr[n].grad) <= GRAD_TOL, (n, rel(p.grad, gr[n].grad))
+            g_ours[n], g_auto[n] = rel(p.grad, gr[n].grad), rel(ga[n].grad, gr[n].grad)
+    worst = max(g_ours, key=g_ours.get)
+    record(f"avth/{C}-{Dh}-{nh}-{nl}-{B}-{T}", dict(out=e_out, out_autocast=a_out, grad=g_ours[worst], grad_name=worst,
+                                                      grad_autocast=max(g_auto.values())))
+    out_tol, grad_tol = AVTH_TOL[(C, Dh, T)]
+    assert e_out <= out_tol and e_out <= 1.25 * a_out + 1e-4, (e_out, a_out)
+    assert g_ours[worst] <= grad_tol and g_ours[worst] <= 1.25 * max(g_auto.values()) + 1e-4, (worst, g_ours[worst], max(g_auto.values()))
 
 
 def test_avth_matches_reference_golden():
@@ -157,12 +206,12 @@ def test_avth_matches_reference_golden():
     m.cuda().eval()
     x = g["x"].clone().cuda().requires_grad_(True)
     past, fut, losses, _ = m(x, (x.shape[0],))
-    assert rel(past, g["past"]) <= OUT_TOL and rel(fut, g["future"]) <= OUT_TOL and rel(losses["feat"], g["feat"]) <= OUT_TOL
+    e_out = max(rel(past, g["past"]), rel(fut, g["future"]), rel(losses["feat"], g["feat"]))
     ((past * g["g_past"].cuda()).sum() + (fut * g["g_future"].cuda()).sum() + losses["feat"].mean()).backward()
-    assert rel(x.grad, g["dx"]) <= GRAD_TOL
-    for n, p in m.named_parameters():
-        if n in g["grads"] and n != "gpt_model.wpe.weight":
-            assert rel(p.grad, g["grads"][n]) <= GRAD_TOL, n
+    e_grad = max([rel(x.grad, g["dx"])] + [rel(p.grad, g["grads"][n]) for n, p in m.named_parameters()
+                                            if n in g["grads"] and n != "gpt_model.wpe.weight"])
+    record("golden/avth", dict(out=e_out, grad=e_grad))
+    assert e_out <= GOLDEN_AVTH_TOL[0] and e_grad <= GOLDEN_AVTH_TOL[1], (e_out, e_grad)
 
 
 def test_avth_rollout_matches_reference_golden():
@@ -189,15 +238,14 @@ def test_full_model_matches_reference_golden():
     m.load_state_dict(g["state"])
     m.cuda().eval()
     out, aux = m(g["video"].cuda(), target_shape=(g["video"].shape[0],))
-    for k in ("logits/action", "past_logits/action", "future", "past"):
-        assert rel(out[k], g["outputs"][k]) <= OUT_TOL, (k, rel(out[k], g["outputs"][k]))
-    assert rel(aux["feat"], g["feat"]) <= OUT_TOL
+    e_out = max([rel(out[k], g["outputs"][k]) for k in ("logits/action", "past_logits/action", "future", "past")] +
+                [rel(aux["feat"], g["feat"])])
     loss = out["logits/action"].square().mean() + out["past_logits/action"].square().mean() + aux["feat"].mean()
-    assert abs(loss.item() - g["loss"].item()) <= OUT_TOL * abs(g["loss"].item())
+    e_loss = abs(loss.item() - g["loss"].item()) / abs(g["loss"].item())
     loss.backward()
-    for n, p in m.named_parameters():
-        if n in g["grads"] and "wpe" not in n:
-            assert rel(p.grad, g["grads"][n]) <= GRAD_TOL, (n, rel(p.grad, g["grads"][n]))
+    e_grad = max(rel(p.grad, g["grads"][n]) for n, p in m.named_parameters() if n in g["grads"] and "wpe" not in n)
+    record("golden/basemodel", dict(out=e_out, loss=e_loss, grad=e_grad))
+    assert e_out <= GOLDEN_BASE_TOL[0] and e_loss <= GOLDEN_BASE_TOL[0] and e_grad <= GOLDEN_BASE_TOL[1], (e_out, e_loss, e_grad)
 
 
 def test_avth_causality_at_full_size():
@@ -268,8 +316,7 @@ def test_direct_grad_mode_and_fused_sgd_match_torch_sgd():
         la = loss_of(a)
         if opt_a is None:
             opt_a = FlatSGD([dp.vit, dp.head], dp.other, lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-3)
-        for p in dp.other:
-            p.grad = None
+        opt_a.zero_grad()        # (also clears the fused torch-owned parameters: func/train.py:221 semantics)
         la.backward()
         dp.finish_backward()
         opt_a.step()

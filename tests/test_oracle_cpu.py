@@ -125,3 +125,24 @@ def test_oracle_avth_rollout_shapes_and_causality():
     past2, _, _, _ = m(x2, (2,))
     assert torch.allclose(past[:, :4], past2[:, :4], atol=1e-6)   # position t only sees frames <= t-1 (shifted by 1)
     assert not torch.allclose(past[:, 4], past2[:, 4], atol=1e-4)
+
+
+def test_oracle_multicrop_matches_reference():
+    """Test-time augmentation (video.ndim == 7: crops folded by BaseModel.forward, models/base_model.py:239-273): the oracle's
+    restatement equals the unmodified reference."""
+    from oracle import base_model as ob
+    from oracle import ref_host
+    if not ref_host.available():
+        pytest.skip("reference checkout not present")
+    torch.manual_seed(0)
+    hk = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32)
+    ref = ref_host.build_reference_model(num_classes=32, model_type="vit_test_patch16_32", backbone_dim=64, head=hk).eval()
+    o = ob.BaseModel("vit_test_patch16_32", 64, 32, head_kwargs=hk).eval()
+    o.load_state_dict({k: v for k, v in ref.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))})
+    v = torch.randn(2, 4, 3, 3, 1, 32, 32)
+    with torch.no_grad():
+        a, la = ref(v, target_shape=(2,))
+        b, lb = o(v, target_shape=(2,))
+    for k in b:
+        assert (a[k] - b[k]).abs().max().item() < 1e-5, k
+    assert (la["feat"] - lb["feat"]).abs().max().item() < 1e-5

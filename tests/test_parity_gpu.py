@@ -1,0 +1,138 @@
+"""Model-level parity beyond the per-module tests: the BASELINE cfg2 shape end to end, test-time augmentation (multi-crop),
+and forward/backward orderings that exercise the activation-workspace leases. Oracle = CPU fp32 restatement (oracle/).
+
+Every comparison records its measured error in gpurun_out/parity_errors.json (when that directory exists), so the
+tolerances below can be kept at <= 1.5x what the path actually achieves."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import base_model as o_base
+from test_modules_gpu import rel, stress_init
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def record(name, value):
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    path = os.path.join(d, "parity_errors.json")
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[name] = value
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+
+
+def _pair(model_type, dim, classes, head_kwargs, init, dropout=0.2):
+    from avt_b200.model import AVTModel
+    torch.manual_seed(0)
+    ref = o_base.BaseModel(model_type, dim, classes, head_kwargs=head_kwargs, dropout=dropout)
+    if init == "stress":
+        stress_init(ref, 7)
+    ours = AVTModel(model_type, dim, classes, head_kwargs=head_kwargs, dropout=dropout)
+    ours.load_state_dict(ref.state_dict())
+    return ours.cuda(), ref
+
+
+def _loss(out, aux, target, sub):
+    return o_base.training_loss(out, aux, target, sub)
+
+
+@pytest.mark.parametrize("init", ["default", "stress"])
+def test_cfg2_full_size_forward_backward_vs_oracle(init):
+    """BASELINE configs[1] at full size: ViT-B/16 + AVT-h (expts/01), 8 clips x 10 frames x 224^2, the training loss of
+    func/train.py:207-217 and its gradients, eval mode (dropout cannot be RNG-matched). `default` = the reference's init."""
+    ours, ref = _pair("vit_base_patch16_224", 768, 3806, None, init)
+    ours.eval()
+    ref.eval()
+    g = torch.Generator().manual_seed(11)
+    B, T = 8, 10
+    video = torch.rand(B, T, 3, 1, 224, 224, generator=g) * 2 - 1
+    target = torch.randint(0, 3806, (B,), generator=g)
+    sub = torch.randint(0, 3806, (B, T, 1), generator=g)
+    sub[torch.rand(B, T, 1, generator=g) < 0.1] = -1
+    out_r, aux_r = ref(video, target_shape=(B,))
+    loss_r = _loss(out_r, aux_r, target, sub)
+    loss_r.backward()
+    out_o, aux_o = ours(video.cuda(), target_shape=(B,))
+    loss_o = _loss(out_o, aux_o, target.cuda(), sub.cuda())
+    loss_o.backward()
+    errs = {k: rel(out_o[k], out_r[k]) for k in ("future", "past", "logits/action", "past_logits/action")}
+    errs["feat"] = rel(aux_o["feat"], aux_r["feat"])
+    errs["loss"] = abs(loss_o.item() - loss_r.item()) / abs(loss_r.item())
+    gr = dict(ref.named_parameters())
+    gerr = {n: rel(p.grad, gr[n].grad) for n, p in ours.named_parameters() if "wpe" not in n}
+    worst = max(gerr, key=gerr.get)
+    errs["worst_grad"] = gerr[worst]
+    record(f"cfg2_full_{init}", dict(errs, worst_grad_name=worst))
+    tol_out, tol_grad = 1.4e-2, 2.1e-2        # 1.5x measured (outputs 9.1e-3, worst gradient 1.4e-2: patch_embed.proj.weight)
+    assert all(v <= tol_out for k, v in errs.items() if k != "worst_grad"), errs
+    assert errs["worst_grad"] <= tol_grad, (worst, errs["worst_grad"])
+
+
+def test_multicrop_tta_eval_and_train_vs_oracle():
+    """video.ndim == 7 (B, #clips, #crops, C, T', H, W): 3 crops averaged (models/base_model.py:239-273). In train mode the
+    three forwards of the same shape each hold their own activation workspace until the single backward."""
+    hk = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32, embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    ours, ref = _pair("vit_test_patch16_32", 64, 32, hk, "stress", dropout=0.0)
+    g = torch.Generator().manual_seed(5)
+    video = torch.randn(2, 4, 3, 3, 1, 32, 32, generator=g)
+    ours.eval()
+    ref.double().eval()
+    with torch.no_grad():
+        oo, lo = ours(video.cuda(), target_shape=(2,))
+        orr, lr = ref(video.double(), target_shape=(2,))
+    e_eval = max(rel(oo[k], orr[k]) for k in orr)
+    ours.train()
+    ref.train()
+    oo, lo = ours(video.cuda(), target_shape=(2,))
+    (oo["logits/action"].square().mean() + oo["past_logits/action"].square().mean() + lo["feat"].mean()).backward()
+    orr, lr = ref(video.double(), target_shape=(2,))
+    (orr["logits/action"].square().mean() + orr["past_logits/action"].square().mean() + lr["feat"].mean()).backward()
+    gr = dict(ref.named_parameters())
+    e_grad = max(rel(p.grad, gr[n].grad) for n, p in ours.named_parameters() if "wpe" not in n)
+    record("multicrop", dict(eval=e_eval, grad=e_grad))
+    assert e_eval <= 1.35e-2 and e_grad <= 2.35e-2, (e_eval, e_grad)      # 1.5x measured (8.9e-3, 1.56e-2)
+
+
+def test_forward_forward_backward_backward_keeps_each_forwards_activations():
+    """Two forwards of the same shape before their backwards (gradient accumulation, the advisor's round-1 finding): the
+    gradients equal those of the two losses computed one after the other."""
+    from avt_b200 import backbone
+    torch.manual_seed(0)
+    m = backbone.create_model("vit_test_patch16_64").cuda()
+    stress_init(m, 3)
+    x1 = torch.randn(3, 3, 64, 64, device="cuda")
+    x2 = torch.randn(3, 3, 64, 64, device="cuda")
+    g1, g2 = torch.randn(3, 128, device="cuda"), torch.randn(3, 128, device="cuda")
+    m(x1).backward(g1)
+    ga = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad()
+    m(x2).backward(g2)
+    gb = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad()
+    y1, y2 = m(x1), m(x2)          # second forward must not overwrite what the first backward reads
+    y1.backward(g1)
+    y2.backward(g2)
+    for n, p in m.named_parameters():
+        assert torch.allclose(p.grad, ga[n] + gb[n], rtol=1e-5, atol=1e-6), n
+    # an eval forward between a train forward and its backward is harmless as well
+    m.zero_grad()
+    y1 = m(x1)
+    with torch.no_grad():
+        m(x2)
+    y1.backward(g1)
+    for n, p in m.named_parameters():
+        assert torch.equal(p.grad, ga[n]), n
+    # retain_graph after another forward of the same shape took the workspace over: loud error, not wrong gradients
+    y1 = m(x1)
+    y1.backward(g1, retain_graph=True)
+    m(x2).backward(g2)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        y1.backward(g1)
