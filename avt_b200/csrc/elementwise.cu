@@ -133,20 +133,32 @@ dropout_apply_kernel(const float* __restrict__ x, int64_t n4, float p, uint64_t 
 // ----------------------------------------------------------------------------- fused SGD step over a flat buffer
 // torch.optim.SGD semantics (dampening 0): g += wd*p; m = first ? g : mom*m + g; g = nesterov ? g + mom*m : m;
 // p -= lr*g; and the bf16 shadow of p used by the GEMMs is refreshed in the same pass (20 B/param instead of the
-// 4 torch foreach passes + a separate down-cast).
+// 4 torch foreach passes + a separate down-cast). Elements [0, lo4*4) use wd_lo (the reference's bias / bn group,
+// func/train.py:704-731), the rest wd. The gradients may be bf16 (the data-parallel payload), lr may live in device
+// memory (a captured step then follows the reference's per-iteration lr schedule without re-capturing).
+template <bool G_BF16>
 __global__ void __launch_bounds__(256)
-sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, bf16* __restrict__ shadow,
-                int64_t n4, float lr, float mom, float wd, int nesterov, int first) {
+sgd_step_kernel(float* __restrict__ p, const void* __restrict__ g, float* __restrict__ m, bf16* __restrict__ shadow,
+                int64_t n4, int64_t lo4, float lr, const float* __restrict__ lr_dev, float mom, float wd, float wd_lo,
+                int nesterov, int first) {
   pdl_enter();
+  if (lr_dev) lr = __ldg(lr_dev);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
-    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 gv;
+    if constexpr (G_BF16) {
+      const uint2 gb = __ldg(reinterpret_cast<const uint2*>(g) + i);
+      gv = make_float4(bf16_lo(gb.x), bf16_hi(gb.x), bf16_lo(gb.y), bf16_hi(gb.y));
+    } else {
+      gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    }
     float4 mv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(m)[i];
+    const float w = i < lo4 ? wd_lo : wd;
     float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w}, ma[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float gg = fmaf(wd, pa[k], ga[k]);
+      float gg = fmaf(w, pa[k], ga[k]);
       ma[k] = first ? gg : fmaf(mom, ma[k], gg);
       gg = nesterov ? fmaf(mom, ma[k], gg) : ma[k];
       pa[k] = fmaf(-lr, gg, pa[k]);
@@ -230,13 +242,21 @@ extern "C" int avt_dropout_apply(const float* x, int64_t n, float p, uint64_t se
   return AVT_OK;
 }
 
-extern "C" int avt_sgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n, float lr, float momentum,
-                            float weight_decay, int nesterov, int first_step, void* stream) {
+extern "C" int avt_sgd_step(float* p, const void* g, int g_is_bf16, float* m, void* p_bf16, int64_t n, float lr,
+                            const float* lr_dev, float momentum, float weight_decay, float weight_decay_lo, int64_t lo_elems,
+                            int nesterov, int first_step, void* stream) {
   AVT_REQUIRE(p && g && m, "null pointer");
-  AVT_REQUIRE(n % 4 == 0, "n must be a multiple of 4 (flat buffers are padded)");
+  AVT_REQUIRE(n % 4 == 0 && lo_elems % 4 == 0, "n and lo_elems must be multiples of 4 (flat buffers are padded)");
+  AVT_REQUIRE(lo_elems >= 0 && lo_elems <= n, "lo_elems out of range");
   if (n <= 0) return AVT_OK;
-  launch_kernel(sgd_step_kernel, dim3(grid_for(n / 4, 256, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      p, g, m, reinterpret_cast<bf16*>(p_bf16), n / 4, lr, momentum, weight_decay, nesterov, first_step);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid(grid_for(n / 4, 256, 8));
+  if (g_is_bf16)
+    launch_kernel(sgd_step_kernel<true>, grid, dim3(256), 0, st, p, g, m, reinterpret_cast<bf16*>(p_bf16), n / 4, lo_elems / 4, lr,
+                  lr_dev, momentum, weight_decay, weight_decay_lo, nesterov, first_step);
+  else
+    launch_kernel(sgd_step_kernel<false>, grid, dim3(256), 0, st, p, g, m, reinterpret_cast<bf16*>(p_bf16), n / 4, lo_elems / 4, lr,
+                  lr_dev, momentum, weight_decay, weight_decay_lo, nesterov, first_step);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }

@@ -39,6 +39,10 @@ class ParamPack:
         off = 0
         self.bias_end = self.small_end = 0
         for n, p in small + big:
+            if p.dim() >= 2 and off == self.small_end:
+                # the vectors end on a 512-element boundary and so does the buffer: the matrix region [small_end, total)
+                # divides into whole 64-element slices for up to 8 ranks (reduce-scatter / sharded optimizer)
+                off = self.small_end = (off + 511) // 512 * 512
             self.names.append(n)
             self.slices[n] = (off, p.numel())
             self.shapes[n] = tuple(p.shape)
@@ -47,11 +51,14 @@ class ParamPack:
                 self.small_end = off
                 if n.endswith("bias"):
                     self.bias_end = off
+        off = (off + 511) // 512 * 512
         self.total = off
         self.device = device
         self.w = torch.zeros(off, dtype=torch.float32, device=device)
         self.g = torch.zeros(off, dtype=torch.float32, device=device)
         self.b = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.gb = None                 # bf16 gradient buffer = the data-parallel payload (enable_bf16_grads)
+        self.matrix_grads_bf16 = False  # weight-gradient GEMMs write straight into gb (no split-K accumulation: AVT-h)
         self.params = {}
         with torch.no_grad():
             for n, p in small + big:
@@ -75,6 +82,29 @@ class ParamPack:
 
     def bv(self, n):
         return self._view(self.b, n)
+
+    def enable_bf16_grads(self, matrices_direct):
+        """Data-parallel mode: gradients leave the GPU as bf16 (792 MB instead of 1.585 GB per step).
+        matrices_direct: the weight-gradient GEMMs store bf16 straight into `gb` (possible when they do not accumulate
+        split-K partial sums in fp32 atomics, i.e. for the 80-row AVT-h); otherwise `g` is down-cast slice by slice."""
+        if self.gb is None:
+            self.gb = torch.zeros(self.total, dtype=torch.bfloat16, device=self.device)
+        self.matrix_grads_bf16 = bool(matrices_direct)
+
+    def fp32_grad_ranges(self):
+        """Element ranges of the MATRIX region whose gradients are produced in fp32 `g` even with bf16 matrix gradients: the
+        matrices listed in `fp32_grad_names` (e.g. the position-embedding table, summed over the batch). (The vectors,
+        [0, small_end), always stay fp32: their gradients come from atomics and the kernels read them from the master.)"""
+        out = []
+        for n in getattr(self, "fp32_grad_names", ()):
+            o, k = self.slices[n]
+            out.append((o, o + (k + _ALIGN - 1) // _ALIGN * _ALIGN))
+        return out
+
+    def grad_out(self, n):
+        """Where a weight-gradient GEMM writes the gradient of matrix `n`."""
+        direct = self.matrix_grads_bf16 and n not in getattr(self, "fp32_grad_names", ())
+        return self._view(self.gb, n) if direct else self._view(self.g, n)
 
     def intact(self):
         """False if someone re-allocated a parameter (e.g. module.to()) so the flat views are stale."""
@@ -104,9 +134,10 @@ class ParamPack:
         self.g.zero_()
 
     def attach_grads(self):
-        """Direct-gradient mode: make every param.grad a view of the flat gradient buffer."""
+        """Direct-gradient mode: make every param.grad a view of the flat gradient buffer (fp32; with bf16 matrix
+        gradients the matrices' .grad stays None - the fused optimizer reads `gb`)."""
         for n, p in self.params.items():
-            p.grad = self.gv(n)
+            p.grad = None if (self.matrix_grads_bf16 and p.dim() >= 2) else self.gv(n)
 
 
 def param_grads(pack, names, params, direct):
@@ -116,9 +147,10 @@ def param_grads(pack, names, params, direct):
     direct=False: standard autograd semantics (accumulation, DDP hooks): views of ONE cloned buffer."""
     if direct:
         for n, p in zip(names, params):
-            if p.requires_grad and p.grad is None:
+            if p.requires_grad and p.grad is None and not (pack.matrix_grads_bf16 and p.dim() >= 2):
                 p.grad = pack.gv(n)
         return (None,) * len(names)
+    assert not pack.matrix_grads_bf16, "bf16 matrix gradients need direct_grads (FlatDataParallel + FlatSGD)"
     g = pack.g.clone()
     out = []
     for n, p in zip(names, params):
@@ -216,13 +248,15 @@ class BlockStack:
         return self._ws_buf
 
     def _wgrad(self, x, dy, wname, bname):
-        dW = self.pack.gv(wname)
+        dW = self.pack.grad_out(wname)
         rows = x.shape[0]
         if self.s.conv1d:   # dW[in, out] = X^T dY
             sk = _split_k_for(x.shape[1], dy.shape[1], rows, 256)
+            assert sk == 1 or dW.dtype == torch.float32
             ops.gemm(x, dy, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed)
         else:               # dW[out, in] = dY^T X; the bias gradient (column sums of dY) rides on the A tiles in smem
             sk = _split_k_for(dy.shape[1], x.shape[1], rows, 256)
+            assert dW.dtype == torch.float32
             ops.gemm(dy, x, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1 and self.grads_prezeroed,
                      a_colsum=self.pack.gv(bname) if bname is not None else None)
             return

@@ -135,6 +135,7 @@ class AVTh(nn.Module):
         self.return_past_too = return_past_too
         self.direct_grads = False
         self._grads_ready_hook = None
+        self._before_forward_hook = None   # FlatDataParallel: wait for the all-gather of the sharded-optimizer weights
         self._pack = None
         self._stack = None
         self._rng_dev = None
@@ -159,6 +160,7 @@ class AVTh(nn.Module):
         self._param_order = [n for n, _ in named]
         self._param_list = [p for _, p in named]
         self._pack = engine.ParamPack(named, device)
+        self._pack.fp32_grad_names = ("gpt_model.wpe.weight",)     # summed over the batch in fp32 (avt_frame_sum_grads)
         spec = engine.StackSpec(dim=self.inter_dim, heads=self.n_head, layers=self.n_layer, eps=self.eps,
                                 act=ops.ACT_GELU_TANH, conv1d=True, causal=True, names=_HF_NAMES,
                                 p_attn=self.attn_pdrop, p_resid=self.resid_pdrop, attn_impl="simt")
@@ -222,7 +224,7 @@ class AVTh(nn.Module):
         a = w["aux"]
         pk.zero_small_grads()
         ops.cast_bf16(ddec.contiguous().float(), a["db"])
-        ops.gemm(a["db"], a["lnf"], pk.gv("decoder.weight"), a_mn=True, b_mn=True)          # dWdec = ddec^T lnf
+        ops.gemm(a["db"], a["lnf"], pk.grad_out("decoder.weight"), a_mn=True, b_mn=True)    # dWdec = ddec^T lnf
         sk = engine.small_m_split(M, Dh, C)
         ops.gemm(a["db"], pk.bv("decoder.weight"), a["dlnf"], b_mn=True, split_k=sk,        # dlnf = ddec Wdec
                  workspace=st._gemm_ws(a["dlnf"], sk))
@@ -235,7 +237,7 @@ class AVTh(nn.Module):
             g32, gb = a["g32"], a["gb"]
             ops.dropout_apply(dx, p_embd, seed, off + (255 << 28), y_f32=g32, y_bf16=gb, offset_dev=off_dev)
         ops.frame_sum_grads(g32, B, T, Dh, a["fsum"], dpos=pk.gv("gpt_model.wpe.weight")[:T], accumulate=False)
-        ops.gemm(gb, a["xb"], pk.gv("encoder.weight"), a_mn=True, b_mn=True)                 # dWenc = g^T feats
+        ops.gemm(gb, a["xb"], pk.grad_out("encoder.weight"), a_mn=True, b_mn=True)           # dWenc = g^T feats
         dfeats = torch.empty(M, C, dtype=torch.float32, device=ddec.device)
         sk = engine.small_m_split(M, C, Dh)
         ops.gemm(gb, pk.bv("encoder.weight"), dfeats, b_mn=True, split_k=sk,                 # dfeats = g Wenc
@@ -302,6 +304,8 @@ class AVTh(nn.Module):
         if output_len < 1:
             raise NotImplementedError("output_len must be >= 1 (the reference's output_len <= 0 returns nothing to decode)")
         B, T, C = feats.shape
+        if self._before_forward_hook is not None:
+            self._before_forward_hook()
         self._ensure_pack(feats.device)
         full_orig_feats = inp_feats = feats
         orig_feats_len = T

@@ -205,8 +205,13 @@ def attention_tc_bwd(qkv, out, dout, lse, dqkv, F, H, N, *, scale):
               _stream())
 
 
-def sgd_step(p, g, m, shadow, lr, momentum, weight_decay, nesterov, first):
-    _chk_cuda(p, g, m, shadow)
-    assert p.dtype == g.dtype == m.dtype == torch.float32 and p.numel() == g.numel() == m.numel()
-    _lib.call("avt_sgd_step", _ptr(p), _ptr(g), _ptr(m), _ptr(shadow), p.numel(), float(lr), float(momentum),
-              float(weight_decay), int(nesterov), int(first), _stream())
+def sgd_step(p, g, m, shadow, lr, momentum, weight_decay, nesterov, first, *, weight_decay_lo=None, lo_elems=0, lr_dev=None):
+    """p, m fp32 flat (or a contiguous shard of a flat buffer); g fp32 or bf16; elements [0, lo_elems) decay with
+    weight_decay_lo; lr_dev: optional fp32 device scalar that overrides lr."""
+    _chk_cuda(p, g, m, shadow, lr_dev)
+    assert p.dtype == m.dtype == torch.float32 and p.numel() == g.numel() == m.numel()
+    assert g.dtype in (torch.float32, torch.bfloat16) and p.is_contiguous() and g.is_contiguous() and m.is_contiguous()
+    _lib.call("avt_sgd_step", _ptr(p), _ptr(g), int(g.dtype == torch.bfloat16), _ptr(m), _ptr(shadow), p.numel(), float(lr),
+              _ptr(lr_dev), float(momentum), float(weight_decay),
+              float(weight_decay if weight_decay_lo is None else weight_decay_lo), int(lo_elems), int(nesterov), int(first),
+              _stream())

@@ -181,7 +181,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if args.comm_sms <= 0:
-        args.comm_sms = 16 if world <= 2 else 24
+        args.comm_sms = 8
     if world > 1:
         os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))   # the all-reduce shares the GPU with the backward
         dist.init_process_group("nccl", device_id=dev)
@@ -200,6 +200,7 @@ def run_ours(args):
 
     def core(video, target, past_tgt):
         """forward -> loss -> backward -> gradient all-reduce -> optimizer step (func/train.py:204-233)"""
+        dp.begin_step()                                              # N > 1: all-gather of the sharded AVT-h weights, under the forward
         out, aux = model(video, target_shape=(B,))
         loss = training_loss(out, aux, target, past_tgt=past_tgt)
         state["acc"] = accuracy(out["logits/action"], target, topk=(1, 5))   # train_eval_ops.py:61-63, every iteration
@@ -207,6 +208,7 @@ def run_ours(args):
             dp.broadcast_parameters()
             state["opt"] = FlatSGD([dp.vit, dp.head], dp.other, lr=1e-4 * world, momentum=0.9, nesterov=True,
                                    weight_decay=1e-6)                 # expts/01:26-28, func/train.py:718
+            state["opt"].use_device_lr(dev)                           # lr schedules stay live under the captured graph
         state["opt"].zero_grad()                                     # func/train.py:221
         loss.backward()
         dp.finish_backward(state["opt"])     # waits for the collectives piecewise and applies the fused SGD in between
@@ -450,9 +452,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python each step")
     ap.add_argument("--comm-sms", type=int, default=0,
-                    help="SMs left to NCCL during the overlapped gradient all-reduce (0 = auto: 16 up to 2 GPUs, 24 beyond - "
-                         "on 8 GPUs the 1.58 GB fp32 all-reduce did not fit under the backward with 16 channels; 124 SMs keep "
-                         "the forward / dgrad GEMMs at the same 12 / 9 / 3 tile rounds as 132)")
+                    help="SMs left to NCCL while the bf16 gradient collectives overlap the backbone backward (0 = auto: 8; the "
+                         "AVT-h reduce-scatter has the whole 8 ms backward for 0.6 GB, the per-layer backbone all-reduces are "
+                         "14 MB each)")
     args = ap.parse_args()
     model, frames, batch = CONFIGS[args.config]
     args.model = args.model or model

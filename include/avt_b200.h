@@ -189,12 +189,17 @@ int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int F, int H, i
 int avt_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int F, int H,
                          int N, float scale, void* stream);
 
-/* One SGD-with-momentum step over a flat parameter buffer, torch.optim.SGD semantics with dampening 0
- * (conf/opt/optimizer/sgd.yaml, expts/01:26-28: momentum 0.9, nesterov, uniform weight decay): p, m updated in
- * place, and the bf16 copy of p read by the GEMMs (p_bf16, may be NULL) refreshed in the same pass.
+/* One SGD-with-momentum step over a flat parameter buffer (or one rank's shard of it), torch.optim.SGD semantics with
+ * dampening 0 (conf/opt/optimizer/sgd.yaml, expts/01:26-28: momentum 0.9, nesterov): p, m updated in place, and the bf16
+ * copy of p read by the GEMMs (p_bf16, may be NULL) refreshed in the same pass.
+ *   g / g_is_bf16      gradients, fp32 or bf16 (the data-parallel gradient payload is bf16)
+ *   weight_decay_lo    weight decay of elements [0, lo_elems): the reference's bias / bn parameter group, whose decay is
+ *                      scaled by opt.bias_bn_wd_scale (func/train.py:704-731); the flat buffers keep biases first
+ *   lr_dev             optional device scalar overriding lr (per-iteration lr schedules under a captured CUDA graph)
  * Replaces optimizer.step() (func/train.py:233) for the flat AVT-b / AVT-h buffers. */
-int avt_sgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n, float lr, float momentum, float weight_decay,
-                 int nesterov, int first_step, void* stream);
+int avt_sgd_step(float* p, const void* g, int g_is_bf16, float* m, void* p_bf16, int64_t n, float lr, const float* lr_dev,
+                 float momentum, float weight_decay, float weight_decay_lo, int64_t lo_elems, int nesterov, int first_step,
+                 void* stream);
 
 #ifdef __cplusplus
 }

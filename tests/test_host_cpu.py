@@ -173,8 +173,10 @@ def test_bench_reads_measured_peaks_in_any_reasonable_schema(tmp_path, monkeypat
 
 
 def test_finish_backward_interleaves_sgd_with_collective_waits():
-    """FlatDataParallel.finish_backward(optimizer): AVT-h buffer first (its all-reduce finished long ago, its update hides
-    the tail of the collective), then the backbone slices, then the torch-owned rest - each update only after ITS waits."""
+    """FlatDataParallel.finish_backward(optimizer): this rank's AVT-h shard first (its reduce-scatter finished long ago, its
+    update hides the tail of the collectives), then the backbone slices, then the torch-owned rest - each update only
+    after ITS waits; the all-gather of the updated bf16 weights is left for the next step's begin_step()."""
+    from avt_b200 import parallel
     from avt_b200.parallel import FlatDataParallel
     log = []
 
@@ -195,62 +197,63 @@ def test_finish_backward_interleaves_sgd_with_collective_waits():
         def step_flat(self, i):
             log.append(f"step_flat {i}")
 
+        def step_flat_vectors(self, i):
+            log.append(f"step_flat_vectors {i}")
+
+        def step_flat_shard(self, i, shard, rng):
+            log.append(f"step_flat_shard {i} {rng}")
+
         def step_other(self):
             log.append("step_other")
 
+    class Pack:
+        total, small_end = 1024, 512
+
+    class Head:
+        _pack = Pack()
+
     dp = FlatDataParallel.__new__(FlatDataParallel)
-    dp.group, dp.comm_sms = None, 0
-    dp.vit, dp.head = object(), object()
+    dp.group, dp.comm_sms, dp.world = None, 0, 1
+    dp.vit, dp.head = object(), Head()
     dp.other = []
     dp._other_handles, dp._other_early = [H("other")], set()
-    dp._head_handles, dp._handles = [H("head")], [H("vit11"), H("vit0"), H("rest")]
+    dp._head_rs, dp._handles = ("shard", H("head")), [H("vit11"), H("vit0"), H("rest")]
+    dp._head_small = [H("head vectors")]
+    dp._shadow_shards_stale = dp._master_stale = False
     dp.finish_backward(Opt([dp.vit, dp.head]))
-    assert log == ["lr", "wait head", "step_flat 1", "wait vit11", "wait vit0", "wait rest", "step_flat 0", "wait other",
-                   "step_other"]
-    assert dp._handles == [] and dp._head_handles == [] and dp._other_handles == []
+    assert log == ["lr", "wait head", "wait head vectors", "step_flat_vectors 1", "step_flat_shard 1 (512, 1024)", "wait vit11", "wait vit0", "wait rest", "step_flat 0",
+                   "wait other", "step_other"]
+    assert dp._handles == [] and dp._head_rs is None and dp._other_handles == []
+    assert dp._shadow_shards_stale and dp._master_stale      # -> begin_step() all-gathers, state_dict() syncs the masters
 
 
-def test_reference_basemodel_hosts_the_dropins():
-    """The drop-in boundary against the REAL glue: the unmodified reference `models.base_model.BaseModel`
-    (models/base_model.py:22-26,65-68) instantiates avt_b200's backbone / head through their Hydra `_target_` paths, ends up
-    with the same parameter names and shapes as with its own modules, `_initialize_weights` (:110-127) gives the same
-    init statistics, and `init_from_model`-style loading (func/train.py:679-688) works. Needs /root/reference (authoring
-    container only); the GPU box skips it."""
-    from oracle import ref_host
-    if not ref_host.available():
-        pytest.skip("reference checkout not present")
-    ref_host.install_stubs()
-    from models.base_model import BaseModel
-    head = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32)
-    torch.manual_seed(0)
-    cfg_ref = ref_host.model_cfg("vit_test_patch16_32", 64, head=head)
-    ref = BaseModel(cfg_ref, {"action": 37}, {})
-    torch.manual_seed(0)
-    cfg = ref_host.model_cfg("vit_test_patch16_32", 64, head=head)
-    cfg["backbone"] = {"_target_": "avt_b200.backbone.TIMMModel", "model_type": "vit_test_patch16_32"}
-    cfg["future_predictor"] = dict(cfg["future_predictor"], _target_="avt_b200.future_prediction.AVTh")
-    ours = BaseModel(cfg, {"action": 37}, {})
-    from avt_b200.backbone import TIMMModel
-    from avt_b200.future_prediction import AVTh
-    assert isinstance(ours.backbone, TIMMModel) and isinstance(ours.future_predictor, AVTh)
-    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
-    b = {k: tuple(v.shape) for k, v in ref.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
-    assert a == b, set(a) ^ set(b)
-    assert sum(p.numel() for p in ours.parameters()) == sum(p.numel() for p in ref.parameters())
-    # BaseModel._initialize_weights re-initialises nn.Linear children: same statistics on both sides
-    for name in ("backbone.model.blocks.0.attn.qkv.weight", "future_predictor.encoder.weight", "classifiers.action.weight"):
-        so, sr = dict(ours.named_parameters())[name].std().item(), dict(ref.named_parameters())[name].std().item()
-        assert abs(so - sr) < 0.15 * sr and abs(sr - 0.01) < 2e-3, (name, so, sr)
-    so = ours.future_predictor.gpt_model.h[0].attn.c_attn.weight.std().item()      # HF Conv1D: untouched, N(0, 0.02)
-    assert abs(so - 0.02) < 4e-3
-    # train.init_from_model=[[backbone.model, ckpt]] -> attrgetter('backbone.model')(model).load_state_dict(sd, strict=False)
-    import operator
-    sd = {k: torch.randn_like(v) for k, v in ref.backbone.model.state_dict().items()}
-    res = operator.attrgetter("backbone.model")(ours).load_state_dict(sd, strict=False)
-    assert not res.missing_keys and not res.unexpected_keys
-    assert torch.equal(ours.backbone.model.blocks[1].mlp.fc1.weight, sd["blocks.1.mlp.fc1.weight"])
-    # whole-model strict resume from a reference checkpoint (func/train.py:764)
-    ours.load_state_dict({k: v for k, v in ref.state_dict().items()}, strict=True)
-    # no CPU path: the reference glue reaches our backbone and gets the loud error, not a silent fallback
-    with pytest.raises(RuntimeError, match="CUDA"):
-        ours(torch.zeros(1, 2, 3, 1, 32, 32), target_shape=(1,))
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from avt_b200.parallel import all_gather_shards_, reduce_scatter_mean, shard_range
+    # gradients: rank r holds r+1 everywhere; the mean is 1.5; every rank keeps only its half
+    g = torch.full((1024,), float(rank + 1)).to(torch.bfloat16)
+    shard, h = reduce_scatter_mean(g)
+    lo, hi = shard_range(1024)
+    # "sharded optimizer": each rank updates only its shard of the weights, then the shards are all-gathered
+    w = torch.zeros(1024)
+    w[lo:hi] = -0.1 * shard.float() + rank
+    all_gather_shards_(w)
+    q.put((rank, (lo, hi), shard.dtype == torch.bfloat16, shard.float().unique().tolist(), w[0].item(), w[-1].item()))
+    dist.destroy_process_group()
+
+
+def test_reduce_scatter_update_all_gather_gloo_world2():
+    """The sharded-optimizer exchange (reduce-scatter mean -> update of the local shard -> all-gather) over gloo, world 2."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res[0][:4] == (0, (0, 512), True, [1.5]) and res[1][:4] == (1, (512, 1024), True, [1.5])
+    for r in res:     # every rank ends with both shards: rank 0's update in front, rank 1's behind
+        assert abs(r[4] - (-0.15)) < 1e-6 and abs(r[5] - 0.85) < 1e-6
