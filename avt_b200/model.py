@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from .backbone import TIMMModel
 from .future_prediction import AVTh
+from .loss_head import FusedClassifierLoss
 
 EXPTS01_HEAD = dict(n_head=4, n_layer=6, output_len=1, inter_dim=2048, return_past_too=True,
                     future_pred_loss={"_target_": "torch.nn.MSELoss"}, future_pred_loss_wt=1.0, avg_last_n=1)
@@ -27,6 +28,7 @@ class AVTModel(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.classifiers = nn.ModuleDict({"action": nn.Linear(backbone_dim, num_classes)})
         self._initialize_weights()
+        self._loss_head = None
 
     def _initialize_weights(self):  # models/base_model.py:110-127
         for m in self.modules():
@@ -53,13 +55,37 @@ class AVTModel(nn.Module):
         losses = {k: torch.mean(torch.stack([d[k] for d in losses], dim=0), dim=0) for k in losses[0]}
         return feats, losses
 
-    def forward_singlecrop(self, video, target_shape=None):
-        """video (B, #clips=T, C, T'=1, H, W) -> (outputs dict, aux_losses dict)  [models/base_model.py:140-220]"""
+    def _features(self, video, target_shape):
         B, num_clips = video.size(0), video.size(1)
         feats = self.backbone(video.flatten(0, 1))                      # base_model.py:153-154
         feats = torch.mean(feats, [-1, -2]).permute((0, 2, 1))          # :157, :166
         feats = feats.reshape((B, num_clips) + feats.shape[1:]).flatten(1, 2)   # :183-191
-        past, future, losses, _ = self.future_predictor(feats, target_shape)    # :196-197
+        return self.future_predictor(feats, target_shape)               # :196-197
+
+    def training_losses(self, video, target, past_target):
+        """The training step's forward with the classifier + cross-entropy head fused (avt_b200.loss_head): the same
+        losses `forward()` + `training_loss()` give, without materialising the logits dictionaries.
+        Returns ({'cls_action', 'past_cls_action', 'feat'}: scalar means as in func/train.py:207-209, {'acc1/action',
+        'acc5/action'}: top-k accuracies of the future logits in percent, func/train_eval_ops.py:61-63)."""
+        past, future, aux, _ = self._features(video, target.shape)
+        if self._loss_head is None or self._loss_head.linear is not self.classifiers["action"]:
+            self._loss_head = FusedClassifierLoss(self.classifiers["action"])
+        p = self.dropout.p if self.training else 0.0
+        lf, lp, acc1, acc5 = self._loss_head(past, future, past_target, target, p)
+        losses = {"cls_action": lf, "past_cls_action": lp}
+        losses.update({k: torch.mean(v) for k, v in aux.items()})
+        return losses, {"acc1/action": acc1, "acc5/action": acc5}
+
+    def attach_loss_head_to(self, optimizer):
+        """Let a FlatSGD keep the classifier's bf16 copy current in its own update pass (valid after one training_losses())."""
+        head = self._loss_head
+        if head is not None and head._wb is not None:
+            w = self.classifiers["action"].weight
+            optimizer.attach_shadow(w, head._wb[:head.classes].view(-1), head.shadow_written_by_optimizer)
+
+    def forward_singlecrop(self, video, target_shape=None):
+        """video (B, #clips=T, C, T'=1, H, W) -> (outputs dict, aux_losses dict)  [models/base_model.py:140-220]"""
+        past, future, losses, _ = self._features(video, target_shape)
         out = {"past": past, "future": future}
         out["past_logits/action"] = self.classifiers["action"](self.dropout(past))     # :203-207
         out["logits/action"] = self.classifiers["action"](self.dropout(future))       # :215-216

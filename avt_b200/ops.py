@@ -215,3 +215,17 @@ def sgd_step(p, g, m, shadow, lr, momentum, weight_decay, nesterov, first, *, we
               _ptr(lr_dev), float(momentum), float(weight_decay),
               float(weight_decay if weight_decay_lo is None else weight_decay_lo), int(lo_elems), int(nesterov), int(first),
               _stream())
+
+
+def softmax_xent(logits, classes, target, loss, *, row_scale=None, rank=None, dlogits=None):
+    """logits fp32 [R, >= classes] (row stride may exceed `classes`), target int64 [R] (-1 = ignored), loss fp32 [R];
+    optional rank int32 [R] and dlogits bf16 [R, classes_padded] = (softmax - onehot) * row_scale."""
+    _chk_cuda(logits, target, loss, row_scale, rank, dlogits)
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and target.dtype == torch.int64 and target.is_contiguous()
+    R = logits.shape[0]
+    assert loss.numel() == R and target.numel() == R
+    if dlogits is not None:
+        assert dlogits.dtype == torch.bfloat16 and dlogits.stride(1) == 1 and row_scale is not None and row_scale.numel() == R
+    _lib.call("avt_softmax_xent", _ptr(logits), logits.stride(0), R, int(classes), _ptr(target), _ptr(row_scale), _ptr(loss),
+              _ptr(rank), _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0,
+              dlogits.shape[1] if dlogits is not None else 0, _stream())

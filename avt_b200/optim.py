@@ -34,11 +34,17 @@ class FlatSGD:
         # torch.optim.SGD with the same hyper-parameters, which also serves lr schedulers through `param_groups`.
         self.fused_other = [p for p in other_params if p.numel() % 4 == 0 and p.numel() >= 1024]
         self.fused_m = [None] * len(self.fused_other)
+        self.shadows = {}      # id(param) -> (bf16 flat view of the same length, callback after the update)
         rest = [p for p in other_params if not any(p is q for q in self.fused_other)]
         groups = [dict(params=[p for p in rest if p.dim() >= 2], weight_decay=weight_decay),
                   dict(params=[p for p in rest if p.dim() < 2], weight_decay=self.wd_bias)]       # 1-D = biases
         groups = [g for g in groups if g["params"]]
         self.other = torch.optim.SGD(groups, lr=lr, momentum=momentum, nesterov=nesterov) if groups else None
+
+    def attach_shadow(self, param, shadow_flat, on_update):
+        """A bf16 copy of a fused torch-owned parameter that the update kernel keeps current (same element order)."""
+        assert shadow_flat.dtype == torch.bfloat16 and shadow_flat.numel() == param.numel() and shadow_flat.is_contiguous()
+        self.shadows[id(param)] = (shadow_flat, on_update)
 
     @property
     def param_groups(self):  # lr schedulers poke at this
@@ -123,10 +129,14 @@ class FlatSGD:
             first = self.fused_m[i] is None
             if first:
                 self.fused_m[i] = torch.empty_like(p.data)
-            assert p.data.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32
+            assert p.data.is_contiguous() and p.dtype == torch.float32
             wd = self.wd if p.dim() >= 2 else self.wd_bias
-            ops.sgd_step(p.data.view(-1), p.grad.view(-1), self.fused_m[i].view(-1), None, self.lr, self.momentum, wd,
-                         self.nesterov, first, lr_dev=self.lr_dev)
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            shadow = self.shadows.get(id(p))      # e.g. the classifier's bf16 copy (avt_b200.loss_head): refreshed in the same pass
+            ops.sgd_step(p.data.view(-1), g.view(-1), self.fused_m[i].view(-1), shadow[0] if shadow else None, self.lr,
+                         self.momentum, wd, self.nesterov, first, lr_dev=self.lr_dev)
+            if shadow:
+                shadow[1]()
         if self.other is not None:
             self.other.step()
 

@@ -201,14 +201,20 @@ def run_ours(args):
     def core(video, target, past_tgt):
         """forward -> loss -> backward -> gradient all-reduce -> optimizer step (func/train.py:204-233)"""
         dp.begin_step()                                              # N > 1: all-gather of the sharded AVT-h weights, under the forward
-        out, aux = model(video, target_shape=(B,))
-        loss = training_loss(out, aux, target, past_tgt=past_tgt)
-        state["acc"] = accuracy(out["logits/action"], target, topk=(1, 5))   # train_eval_ops.py:61-63, every iteration
+        if args.fused_loss_head:
+            # CE(future) + CE(past) + top-1/5 accuracy through the fused classifier head (avt_b200.loss_head), MSE feat as is
+            losses, state["acc"] = model.training_losses(video, target, past_tgt)
+            loss = sum(losses.values())                              # loss weights 1/1/1 (expts/01:1-2)
+        else:
+            out, aux = model(video, target_shape=(B,))
+            loss = training_loss(out, aux, target, past_tgt=past_tgt)
+            state["acc"] = accuracy(out["logits/action"], target, topk=(1, 5))   # train_eval_ops.py:61-63, every iteration
         if state["opt"] is None:                                     # flat buffers exist after the first forward
             dp.broadcast_parameters()
             state["opt"] = FlatSGD([dp.vit, dp.head], dp.other, lr=1e-4 * world, momentum=0.9, nesterov=True,
                                    weight_decay=1e-6)                 # expts/01:26-28, func/train.py:718
             state["opt"].use_device_lr(dev)                           # lr schedules stay live under the captured graph
+            model.attach_loss_head_to(state["opt"])
         state["opt"].zero_grad()                                     # func/train.py:221
         loss.backward()
         dp.finish_backward(state["opt"])     # waits for the collectives piecewise and applies the fused SGD in between
@@ -451,6 +457,8 @@ def main():
     ap.add_argument("--model", default=None, help="timm model_type (default: the preset's)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python each step")
+    ap.add_argument("--no-fused-loss-head", dest="fused_loss_head", action="store_false",
+                    help="classifier + cross-entropy + accuracy as ~40 eager torch launches (the round-1 path)")
     ap.add_argument("--comm-sms", type=int, default=0,
                     help="SMs left to NCCL while the bf16 gradient collectives overlap the backbone backward (0 = auto: 8; the "
                          "AVT-h reduce-scatter has the whole 8 ms backward for 0.6 GB, the per-layer backbone all-reduces are "

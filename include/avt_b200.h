@@ -189,6 +189,15 @@ int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int F, int H, i
 int avt_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int F, int H,
                          int N, float scale, void* stream);
 
+/* Row-wise softmax cross-entropy over classifier logits, forward and gradient in one pass (one CTA per row, the row in
+ * registers): loss[r] = logsumexp(l) - l[target[r]] (0 when target < 0: nn.CrossEntropyLoss(ignore_index=-1,
+ * reduction='none'), loss_fn/multidim_xentropy.py:10-25 via func/train_eval_ops.py:57-85), rank[r] = number of classes
+ * with a larger logit than the target's (top-k correct <=> rank < k: common/utils.py:17-44; `classes` for ignored rows),
+ * dlogits[r] (bf16, may be NULL; columns [classes, classes_padded) zeroed) = (softmax(l) - onehot) * row_scale[r].
+ * logits fp32 [rows, classes] with row stride ld; classes <= 4096. Replaces ~40 ATen launches of the reference step. */
+int avt_softmax_xent(const float* logits, int64_t ld, int rows, int classes, const int64_t* target, const float* row_scale,
+                     float* loss, int* rank, void* dlogits_bf16, int64_t ldd, int classes_padded, void* stream);
+
 /* One SGD-with-momentum step over a flat parameter buffer (or one rank's shard of it), torch.optim.SGD semantics with
  * dampening 0 (conf/opt/optimizer/sgd.yaml, expts/01:26-28: momentum 0.9, nesterov): p, m updated in place, and the bf16
  * copy of p read by the GEMMs (p_bf16, may be NULL) refreshed in the same pass.

@@ -136,3 +136,90 @@ def test_forward_forward_backward_backward_keeps_each_forwards_activations():
     m(x2).backward(g2)
     with pytest.raises(RuntimeError, match="overwritten"):
         y1.backward(g1)
+
+
+@pytest.mark.parametrize("B,T,K,C,p", [(8, 10, 768, 3806, 0.0), (3, 4, 64, 37, 0.0), (8, 15, 768, 3806, 0.0), (8, 10, 768, 3806, 0.2)])
+def test_fused_classifier_loss_vs_torch(B, T, K, C, p):
+    """avt_b200.loss_head (dropout -> classifier GEMM -> softmax-CE fwd+bwd -> gradient GEMMs) against the reference's
+    arithmetic in fp64: F.linear + CrossEntropyLoss(ignore_index=-1, reduction='none') means + top-k accuracy
+    (models/base_model.py:203-216, func/train_eval_ops.py:57-85, common/utils.py:17-44)."""
+    import torch.nn.functional as F
+    from avt_b200.loss_head import FusedClassifierLoss
+    from avt_b200.model import accuracy
+    g = torch.Generator().manual_seed(B * 100 + T)
+    lin = torch.nn.Linear(K, C)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(C, K, generator=g) * 0.05)
+        lin.bias.copy_(torch.randn(C, generator=g) * 0.1)
+    past = torch.randn(B, T, K, generator=g)
+    fut = torch.randn(B, K, generator=g)
+    tgt = torch.randint(0, C, (B,), generator=g)
+    ptgt = torch.randint(0, C, (B, T), generator=g)
+    ptgt[torch.rand(B, T, generator=g) < 0.15] = -1
+    tgt[0] = -1
+    lin_c = torch.nn.Linear(K, C).cuda()
+    lin_c.load_state_dict(lin.state_dict())
+    head = FusedClassifierLoss(lin_c)
+    pc, fc = past.cuda().requires_grad_(True), fut.cuda().requires_grad_(True)
+    lf, lp, a1, a5 = head(pc, fc, ptgt.cuda(), tgt.cuda(), p)
+    (lf + lp).backward()
+    if p > 0.0:      # masks cannot be matched: finite, a fresh mask per call, and unbiased on average
+        assert torch.isfinite(lf) and torch.isfinite(pc.grad).all() and torch.isfinite(lin_c.weight.grad).all()
+        frac = (pc.grad == 0).float().mean().item()
+        assert 0.1 < frac < 0.45                     # ~p of the input gradient is masked (+ rows whose label is ignored)
+        lf2, _, _, _ = head(pc.detach(), fc.detach(), ptgt.cuda(), tgt.cuda(), p)
+        assert lf2.item() != lf.item()
+        return
+    lin64 = lin.double()
+    p64, f64 = past.double().requires_grad_(True), fut.double().requires_grad_(True)
+    lo_f, lo_p = lin64(f64), lin64(p64)
+    rf = F.cross_entropy(lo_f, tgt, ignore_index=-1, reduction="none").mean()
+    rp = F.cross_entropy(lo_p.flatten(0, 1), ptgt.flatten(), ignore_index=-1, reduction="none").mean()
+    (rf + rp).backward()
+    r1, r5 = accuracy(lo_f, tgt, topk=(1, min(5, C)))
+    errs = dict(loss_f=abs(lf.item() - rf.item()) / abs(rf.item()), loss_p=abs(lp.item() - rp.item()) / abs(rp.item()),
+                dW=rel(lin_c.weight.grad, lin64.weight.grad), db=rel(lin_c.bias.grad, lin64.bias.grad),
+                dpast=rel(pc.grad, p64.grad), dfut=rel(fc.grad, f64.grad))
+    record(f"loss_head/{B}-{T}-{K}-{C}", errs)
+    # bf16 operands for the classifier GEMMs (like every other GEMM of the path): logits to ~3e-3, gradients to ~5e-3
+    assert errs["loss_f"] < 4e-4 and errs["loss_p"] < 4e-4, errs                    # 1.5x measured (2.3e-4)
+    assert max(errs["dW"], errs["db"], errs["dpast"], errs["dfut"]) < 6e-3, errs   # 1.5x measured (3.9e-3)
+    assert abs(a1.item() - r1.item()) < 1e-3 and abs(a5.item() - r5.item()) < 1e-3
+    # ignored rows contribute nothing
+    assert torch.count_nonzero(fc.grad[0]) == 0
+
+
+def test_training_losses_fused_head_equals_forward_plus_loss():
+    """AVTModel.training_losses (fused classifier / cross-entropy head) == forward() + training_loss() + accuracy() of the
+    same model, and both match the oracle; gradients included (eval mode: no dropout)."""
+    from avt_b200.model import accuracy, past_targets, training_loss
+    hk = dict(n_head=2, n_layer=2, inter_dim=64, n_positions=32)
+    ours, ref = _pair("vit_test_patch16_32", 64, 37, hk, "stress")
+    ours.eval()
+    ref.double().eval()
+    g = torch.Generator().manual_seed(9)
+    B, T = 4, 6
+    video = torch.randn(B, T, 3, 1, 32, 32, generator=g)
+    target = torch.randint(0, 37, (B,), generator=g)
+    sub = torch.randint(0, 37, (B, T, 1), generator=g)
+    sub[torch.rand(B, T, 1, generator=g) < 0.2] = -1
+    losses, accs = ours.training_losses(video.cuda(), target.cuda(), past_targets(sub.cuda()))
+    fused = sum(losses.values())
+    fused.backward()
+    g_fused = {n: p.grad.clone() for n, p in ours.named_parameters()}
+    ours.zero_grad()
+    out, aux = ours(video.cuda(), target_shape=(B,))
+    plain = training_loss(out, aux, target.cuda(), sub.cuda())
+    plain.backward()
+    a1, a5 = accuracy(out["logits/action"], target.cuda(), topk=(1, 5))
+    assert abs(fused.item() - plain.item()) <= 2e-3 * abs(plain.item())
+    assert abs(accs["acc1/action"].item() - a1.item()) < 1e-3 and abs(accs["acc5/action"].item() - a5.item()) < 1e-3
+    out_r, aux_r = ref(video.double(), target_shape=(B,))
+    loss_r = o_base.training_loss(out_r, aux_r, target, sub)
+    loss_r.backward()
+    gr = dict(ref.named_parameters())
+    e_loss = abs(fused.item() - loss_r.item()) / abs(loss_r.item())
+    e_grad = max(rel(g_fused[n], gr[n].grad) for n in g_fused if "wpe" not in n)
+    e_grad_plain = max(rel(p.grad, gr[n].grad) for n, p in ours.named_parameters() if "wpe" not in n)
+    record("training_losses_fused", dict(loss=e_loss, grad=e_grad, grad_unfused=e_grad_plain))
+    assert e_loss <= 5e-3 and e_grad <= max(2.9e-2, 1.3 * e_grad_plain), (e_loss, e_grad, e_grad_plain)
