@@ -95,6 +95,7 @@ class VisionTransformer(nn.Module):
             if isinstance(m, nn.Linear):
                 nn.init.trunc_normal_(m.weight, std=0.02)
                 nn.init.zeros_(m.bias)
+        self.precision = "bf16"     # "fp32": inference in fp32 on the CUDA cores (north star's 1e-5 bound; engine.forward_fp32)
         self.direct_grads = False   # True: backward writes param.grad (views of one flat buffer) itself
         self._grads_ready_hook = None  # called at the end of backward (parallel.FlatDataParallel)
         self.attn_impl = "tc"
@@ -129,7 +130,26 @@ class VisionTransformer(nn.Module):
         self._ensure_pack(x.device)
         # (grad mode is off inside autograd.Function.forward, so decide here whether to keep activations)
         train = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
+        if self.precision == "fp32":
+            if train:
+                raise NotImplementedError("precision='fp32' is the inference-only validation mode: call it under torch.no_grad()")
+            return self._run_forward_fp32(x)
         return _ViTFunction.apply(x, self, train, *self._param_list)
+
+    def _run_forward_fp32(self, x):
+        pk, st = self._pack, self._stack
+        F, ntok, D = x.shape[0], self.num_tokens, self.embed_dim
+        Kp = self.in_chans * self.patch_size ** 2
+        x = x.contiguous().float()
+        A = torch.empty(F * ntok, Kp, dtype=torch.float32, device=x.device)
+        ops.patchify_f32(x, A, self.patch_size)
+        h = torch.empty(F * ntok, D, dtype=torch.float32, device=x.device)
+        ops.sgemm_f32(A, pk.wv("patch_embed.proj.weight").view(D, Kp), h, bias=pk.wv("patch_embed.proj.bias"),
+                      pos=pk.wv("pos_embed").view(ntok, D), cls=pk.wv("cls_token").view(D), pos_period=ntok)
+        h = st.forward_fp32(h, F, ntok)
+        feats = torch.empty(F, D, dtype=torch.float32, device=x.device)
+        ops.layernorm_fwd(h, pk.wv("norm.weight"), pk.wv("norm.bias"), 1e-6, feats, rows=F, x_stride=ntok * D)   # CLS rows
+        return feats
 
     # ------------------------------------------------------------------ kernels
     def _run_forward(self, x, train):

@@ -378,6 +378,30 @@ class BlockStack:
             ops.attention_simt_bwd(qkv, att, dout, lse, dqkv, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
                                    seed=seed, offset=off, offset_dev=off_dev)
 
+    # ------------------------------------------------------------------ fp32-accuracy mode (inference)
+    def forward_fp32(self, x, nb, ntok):
+        """All blocks in fp32 on x fp32 [M, D] (updated in place and returned): LayerNorm -> qkv -> attention -> proj (+x) ->
+        LayerNorm -> fc1 + GELU -> fc2 (+x), CUDA-core kernels of csrc/fp32_path.cu, weights read from the fp32 masters.
+        The validation path behind the north star's 1e-5 (fp32) bound; no dropout, no activations kept (eval / no_grad)."""
+        s, pk = self.s, self.pack
+        M, D = x.shape
+        hd = D // s.heads
+        f32 = dict(dtype=torch.float32, device=x.device)
+        ln, qkv, att, h = (torch.empty(M, D, **f32), torch.empty(M, 3 * D, **f32), torch.empty(M, D, **f32),
+                           torch.empty(M, 4 * D, **f32))
+        for i in range(s.layers):
+            nm = {k: v.format(i=i) for k, v in s.names.items()}
+            W = lambda k: pk.wv(nm[k] + ".weight")
+            Bv = lambda k: pk.wv(nm[k] + ".bias")
+            ops.layernorm_fwd(x, W("ln1"), Bv("ln1"), s.eps, ln)
+            ops.sgemm_f32(ln, W("qkv"), qkv, b_kn=s.conv1d, bias=Bv("qkv"))
+            ops.attention_f32_fwd(qkv, att, nb, s.heads, ntok, hd, causal=s.causal, scale=hd ** -0.5)
+            ops.sgemm_f32(att, W("proj"), x, b_kn=s.conv1d, bias=Bv("proj"), residual=x)
+            ops.layernorm_fwd(x, W("ln2"), Bv("ln2"), s.eps, ln)
+            ops.sgemm_f32(ln, W("fc1"), h, b_kn=s.conv1d, bias=Bv("fc1"), act=s.act)
+            ops.sgemm_f32(h, W("fc2"), x, b_kn=s.conv1d, bias=Bv("fc2"), residual=x)
+        return x
+
     # ------------------------------------------------------------------ backward
     def backward(self, w, dx, dxb, top_bias_done=False):
         """dx fp32 [M, D] / dxb bf16 copy: gradient w.r.t. the stack output (updated in place to the gradient

@@ -133,6 +133,7 @@ class AVTh(nn.Module):
         self.avg_last_n, self.inter_dim, self.in_features = avg_last_n, inter_dim, in_features
         self.future_pred_loss = _instantiate_loss(future_pred_loss)
         self.return_past_too = return_past_too
+        self.precision = "bf16"            # "fp32": inference in fp32 on the CUDA cores (engine.forward_fp32)
         self.direct_grads = False
         self._grads_ready_hook = None
         self._before_forward_hook = None   # FlatDataParallel: wait for the all-gather of the sharded-optimizer weights
@@ -215,6 +216,18 @@ class AVTh(nn.Module):
         sk = engine.small_m_split(M, C, Dh)
         ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded, split_k=sk, workspace=st._gemm_ws(decoded, sk))
         return decoded, (w, st.lease(w) if train_graph else None, xf, B, T, p_embd, seed, off, off_dev)
+
+    def _run_forward_fp32(self, feats2d, B, T):
+        pk, st = self._pack, self._stack
+        M, C, Dh = B * T, self.in_features, self.inter_dim
+        x = torch.empty(M, Dh, dtype=torch.float32, device=feats2d.device)
+        ops.sgemm_f32(feats2d.contiguous().float(), pk.wv("encoder.weight"), x, pos=pk.wv("gpt_model.wpe.weight")[:T], pos_period=T)
+        x = st.forward_fp32(x, B, T)
+        lnf = torch.empty_like(x)
+        ops.layernorm_fwd(x, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, lnf)
+        decoded = torch.empty(M, C, dtype=torch.float32, device=x.device)
+        ops.sgemm_f32(lnf, pk.wv("decoder.weight"), decoded)
+        return decoded
 
     def _run_backward(self, saved, ddec):
         pk, st = self._pack, self._stack
@@ -310,7 +323,11 @@ class AVTh(nn.Module):
         full_orig_feats = inp_feats = feats
         orig_feats_len = T
         train_graph = torch.is_grad_enabled() and (feats.requires_grad or any(p.requires_grad for p in self._param_list))
-        if output_len == 1:
+        if self.precision == "fp32":
+            if train_graph or self.training or output_len != 1:
+                raise NotImplementedError("precision='fp32' is the inference-only validation mode (eval(), no_grad, output_len 1)")
+            decoded = self._run_forward_fp32(feats.reshape(B * T, C), B, T).view(B, T, C)
+        elif output_len == 1:
             decoded = _HeadFunction.apply(feats.reshape(B * T, C), self, B, T, train_graph, *self._param_list).view(B, T, C)
         else:
             if train_graph or self.training:

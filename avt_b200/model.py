@@ -55,6 +55,13 @@ class AVTModel(nn.Module):
         losses = {k: torch.mean(torch.stack([d[k] for d in losses], dim=0), dim=0) for k in losses[0]}
         return feats, losses
 
+    def set_precision(self, precision):
+        """'bf16' (tensor-core product path) or 'fp32' (inference-only validation path on the CUDA cores, 1e-5 vs the oracle)."""
+        assert precision in ("bf16", "fp32")
+        self.backbone.model.precision = precision
+        self.future_predictor.precision = precision
+        return self
+
     def _features(self, video, target_shape):
         B, num_clips = video.size(0), video.size(1)
         feats = self.backbone(video.flatten(0, 1))                      # base_model.py:153-154

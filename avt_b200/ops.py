@@ -229,3 +229,30 @@ def softmax_xent(logits, classes, target, loss, *, row_scale=None, rank=None, dl
     _lib.call("avt_softmax_xent", _ptr(logits), logits.stride(0), R, int(classes), _ptr(target), _ptr(row_scale), _ptr(loss),
               _ptr(rank), _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0,
               dlogits.shape[1] if dlogits is not None else 0, _stream())
+
+
+# ----------------------------------------------------------------------------- fp32-accuracy mode (inference)
+def sgemm_f32(a, b, out, *, b_kn=False, bias=None, residual=None, act=ACT_NONE, pos=None, cls=None, pos_period=0):
+    """out[M,N] = act(a[M,K] @ Bop + bias) + residual, all fp32; b is [N,K] (nn.Linear) or, with b_kn, [K,N] (HF Conv1D)."""
+    _chk_cuda(a, b, out, bias, residual, pos, cls)
+    assert a.dtype == b.dtype == out.dtype == torch.float32 and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[1] if b_kn else b.shape[0]
+    assert (b.shape[0] if b_kn else b.shape[1]) == K and tuple(out.shape) == (M, N)
+    _lib.call("avt_sgemm_f32", _ptr(a), a.stride(0), _ptr(b), b.stride(0), int(b_kn), M, N, K, _ptr(bias), _ptr(residual),
+              residual.stride(0) if residual is not None else 0, act, _ptr(pos), _ptr(cls), pos_period, _ptr(out), out.stride(0),
+              _stream())
+    return out
+
+
+def attention_f32_fwd(qkv, out, B, H, N, hd, *, causal, scale):
+    _chk_cuda(qkv, out)
+    assert qkv.dtype == out.dtype == torch.float32 and qkv.is_contiguous() and out.is_contiguous()
+    _lib.call("avt_attention_f32_fwd", _ptr(qkv), _ptr(out), B, H, N, hd, int(causal), float(scale), _stream())
+
+
+def patchify_f32(video, out, patch):
+    _chk_cuda(video, out)
+    F, Cc, H, W = video.shape
+    assert video.is_contiguous() and video.dtype == out.dtype == torch.float32
+    _lib.call("avt_patchify_f32", _ptr(video), _ptr(out), F, Cc, H, W, patch, _stream())

@@ -189,6 +189,18 @@ int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int F, int H, i
 int avt_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int F, int H,
                          int N, float scale, void* stream);
 
+/* fp32-accuracy mode (inference; BASELINE.json north star: "within 1e-5 (fp32)"): the same operators on the CUDA cores in
+ * fp32, exact erf / tanh GELU. A validation path for the restated arithmetic, not the product path.
+ * avt_sgemm_f32: out[m,n] = act(sum_k A[m,k] * Bop[k,n] + bias[n]) + residual[m,n]; B stored [N,K] (b_kn = 0, nn.Linear)
+ * or [K,N] (b_kn = 1, HF Conv1D); pos / cls / pos_period as in avt_epilogue_t (patch / frame embedding).
+ * avt_attention_f32_fwd: softmax(q k^T * scale [causal]) v from packed fp32 qkv [B*N, 3*H*hd] -> out [B*N, H*hd].
+ * avt_patchify_f32: video fp32 [F,C,H,W] -> patch rows [F*(P+1), C*patch*patch] (zero rows in the cls slots). */
+int avt_sgemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int b_kn, int M, int N, int K, const float* bias,
+                  const float* residual, int64_t ldr, int act, const float* pos, const float* cls, int pos_period, float* out,
+                  int64_t ldo, void* stream);
+int avt_attention_f32_fwd(const float* qkv, float* out, int B, int H, int N, int hd, int causal, float scale, void* stream);
+int avt_patchify_f32(const float* video, float* out, int F, int C, int H, int W, int patch, void* stream);
+
 /* Row-wise softmax cross-entropy over classifier logits, forward and gradient in one pass (one CTA per row, the row in
  * registers): loss[r] = logsumexp(l) - l[target[r]] (0 when target < 0: nn.CrossEntropyLoss(ignore_index=-1,
  * reduction='none'), loss_fn/multidim_xentropy.py:10-25 via func/train_eval_ops.py:57-85), rank[r] = number of classes
