@@ -63,12 +63,14 @@ SIGNATURES = {
     "avt_colsum_bf16": [_vp, _i64, _i32, _i64, _vp, _vp],
     "avt_frame_sum_grads": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "avt_dropout_apply": [_vp, _i64, _f32, _u64, _u64, _vp, _vp, _vp, _vp],
+    "avt_preprocess_u8": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _f32, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp],
     "avt_sgemm_f32": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
     "avt_attention_f32_fwd": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "avt_patchify_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "avt_softmax_xent": [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "avt_sgd_step": [_vp, _vp, _i32, _vp, _vp, _i64, _f32, _vp, _f32, _f32, _f32, _i64, _i32, _i32, _vp],
     "avt_attention_simt_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp, _vp],
+    "avt_attention_simt_decode": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "avt_attention_tc_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
     "avt_attention_tc_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
     "avt_attention_simt_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp, _vp],

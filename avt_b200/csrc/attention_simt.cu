@@ -24,6 +24,7 @@ struct AttnParams {
   bf16* dqkv;        // bwd: [B*N, 3*Dm]
   int B, H, N, hd, Dm;
   int causal;
+  int q_row;         // fwd: >= 0 -> only this query row of every (batch, head) is computed (KV-cached decode step); -1 = all rows
   float scale;
   float drop_p;
   uint64_t seed, offset;
@@ -107,7 +108,11 @@ __global__ void __launch_bounds__(kAttWarps * 32) attn_fwd_simt_kernel(const Att
   float* s = sS + warp * N;
   const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const uint64_t rng_off = att_offset(p);
-  for (int i = blockIdx.y * kAttWarps + warp; i < N; i += gridDim.y * kAttWarps) {
+  // decode step: the packed qkv buffer IS the KV cache (rows 0..q_row of every batch item are valid, later rows are not
+  // read: causal); only the newest row queries it
+  const int i_begin = p.q_row >= 0 ? p.q_row + (int)(blockIdx.y * kAttWarps + warp) * N : blockIdx.y * kAttWarps + warp;
+  const int i_step = p.q_row >= 0 ? N : gridDim.y * kAttWarps;
+  for (int i = i_begin; i < N; i += i_step) {
     float2 q[NP];
     load_row<NP>(base + (int64_t)i * ld, hd, lane, q);
     const int jmax = p.causal ? i + 1 : N;
@@ -329,11 +334,23 @@ static int check_attn(const AttnParams& p) {
   return AVT_OK;
 }
 
+extern "C" int avt_attention_simt_decode(const void* qkv_cache, void* out, int B, int H, int N, int hd, int q_row, float scale,
+                                         void* stream) {
+  AVT_REQUIRE(qkv_cache && out, "null pointer");
+  AVT_REQUIRE(q_row >= 0 && q_row < N, "q_row must be a row of the cache");
+  AttnParams p{};
+  p.qkv = reinterpret_cast<const bf16*>(qkv_cache); p.out = reinterpret_cast<bf16*>(out); p.lse = nullptr;
+  p.B = B; p.H = H; p.N = N; p.hd = hd; p.Dm = H * hd; p.causal = 1; p.scale = scale; p.q_row = q_row;
+  if (int rc = check_attn(p)) return rc;
+  return dispatch_simt(p, false, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int avt_attention_simt_fwd(const void* qkv, void* out, float* lse, int B, int H, int N, int hd, int causal,
                                       float scale, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                                       void* stream) {
   AVT_REQUIRE(qkv && out, "null pointer");
   AttnParams p{};
+  p.q_row = -1;
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.out = reinterpret_cast<bf16*>(out); p.lse = lse;
   p.B = B; p.H = H; p.N = N; p.hd = hd; p.Dm = H * hd; p.causal = causal; p.scale = scale;
   p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.offset_dev = offset_dev;
@@ -346,6 +363,7 @@ extern "C" int avt_attention_simt_bwd(const void* qkv, const void* out, const vo
                                       uint64_t offset, const uint64_t* offset_dev, void* stream) {
   AVT_REQUIRE(qkv && out && dout && lse && dqkv, "null pointer");
   AttnParams p{};
+  p.q_row = -1;
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.dout = reinterpret_cast<const bf16*>(dout);
   p.o = reinterpret_cast<const bf16*>(out);
   p.lse = const_cast<float*>(lse); p.dqkv = reinterpret_cast<bf16*>(dqkv);

@@ -169,6 +169,28 @@ sgd_step_kernel(float* __restrict__ p, const void* __restrict__ g, float* __rest
   }
 }
 
+// ----------------------------------------------------------------------------- input pipeline: uint8 frames -> normalised fp32 crop
+// The reference's per-frame transform chain after decoding / resizing (func/train.py:550-584, common/transforms.py):
+// ToTensorVideo (uint8 HWC -> float CHW / 255), RandomHorizontalFlipVideo, x * scale_pix_val, NormalizeVideo(mean, std),
+// RandomCropVideo / a fixed crop - one pass on the GPU, so the step's host-to-device copy is the uint8 frames (4x fewer bytes)
+// and the CPU workers stop at decode + resize. out[f, c, y, x] = (in[f, cy + y, cx + (flip ? w-1-x : x), c] / 255 * scale - mean[c]) / std[c]
+// with the crop taken after the flip, as in the reference's order (flip, ..., normalize, crop).
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ in, int F, int Hin, int Win, float* __restrict__ out, int h, int w, int cy, int cx,
+                     const uint8_t* __restrict__ flip, float scale, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_enter();
+  const int64_t total = (int64_t)F * h * w;
+  const float mean[3] = {m0, m1, m2}, inv[3] = {1.f / s0, 1.f / s1, 1.f / s2};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i % w, y = (i / w) % h, f = i / ((int64_t)w * h);
+    const int sx = (flip && flip[f]) ? Win - 1 - (cx + x) : cx + x;
+    const uint8_t* px = in + (((int64_t)f * Hin + cy + y) * Win + sx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      out[(((int64_t)f * 3 + c) * h + y) * w + x] = (px[c] * (scale / 255.0f) - mean[c]) * inv[c];
+  }
+}
+
 static int grid_for(int64_t work_items, int threads, int per_sm) {
   int64_t b = (work_items + threads - 1) / threads;
   const int64_t cap = (int64_t)num_sms() * per_sm;
@@ -257,6 +279,17 @@ extern "C" int avt_sgd_step(float* p, const void* g, int g_is_bf16, float* m, vo
   else
     launch_kernel(sgd_step_kernel<false>, grid, dim3(256), 0, st, p, g, m, reinterpret_cast<bf16*>(p_bf16), n / 4, lo_elems / 4, lr,
                   lr_dev, momentum, weight_decay, weight_decay_lo, nesterov, first_step);
+  AVT_CUDA_OK(cudaGetLastError());
+  return AVT_OK;
+}
+
+extern "C" int avt_preprocess_u8(const uint8_t* frames, int F, int Hin, int Win, float* out, int h, int w, int crop_y, int crop_x,
+                                 const uint8_t* flip, float scale, const float* mean3, const float* std3, void* stream) {
+  AVT_REQUIRE(frames && out && mean3 && std3, "null pointer");
+  AVT_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + h <= Hin && crop_x + w <= Win, "crop outside the frame");
+  if (F <= 0) return AVT_OK;
+  launch_kernel(preprocess_u8_kernel, dim3(grid_for((int64_t)F * h * w, 256, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                frames, F, Hin, Win, out, h, w, crop_y, crop_x, flip, scale, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }

@@ -378,6 +378,40 @@ class BlockStack:
             ops.attention_simt_bwd(qkv, att, dout, lse, dqkv, nb, s.heads, ntok, hd, causal=s.causal, scale=scale, drop_p=p,
                                    seed=seed, offset=off, offset_dev=off_dev)
 
+    # ------------------------------------------------------------------ KV-cached decode (evaluation-time rollout)
+    def decode_step(self, x, caches, att, nb, tmax, pos):
+        """One new token per batch item through all blocks: x fp32 [nb, D] = its input embedding (updated in place to the
+        stack output BEFORE the final LayerNorm, the pending MLP branch in `y`: returns (x_mid, y) like forward()).
+        caches[l] bf16 [nb*tmax, 3D]: layer l's packed qkv rows of all earlier positions (the prefill pass wrote rows
+        0..T-1); the new token's q/k/v go to row `pos` of every item and only that row attends (avt_attention_simt_decode).
+        att bf16 [nb*tmax, D]: attention output scratch. The reference does the same with HF GPT2Model's past_key_values
+        (models/future_prediction.py:168-202)."""
+        s, pk = self.s, self.pack
+        D = s.dim
+        hd = D // s.heads
+        dev = x.device
+        bf = torch.bfloat16
+        ln = torch.empty(nb, D, dtype=bf, device=dev)
+        h = torch.empty(nb, 4 * D, dtype=bf, device=dev)
+        y = torch.empty(nb, D, dtype=bf, device=dev)
+        xmid = torch.empty_like(x)
+        xin = x
+        for i in range(s.layers):
+            nm = {k: v.format(i=i) for k, v in s.names.items()}
+            g1, b1 = pk.wv(nm["ln1"] + ".weight"), pk.wv(nm["ln1"] + ".bias")
+            if i == 0:
+                ops.layernorm_fwd(xin, g1, b1, s.eps, ln)
+            else:       # x_in = x_mid(prev) + mlp branch(prev), fused with this layer's LN1
+                ops.layernorm_fwd(xmid, g1, b1, s.eps, ln, add=y, x_out=xin)
+            qkv_row = caches[i].view(nb, tmax, 3 * D)[:, pos]                 # [nb, 3D], row stride tmax * 3D
+            self._fwd(ln, nm["qkv"] + ".weight", qkv_row, bias=pk.wv(nm["qkv"] + ".bias"))
+            ops.attention_simt_decode(caches[i], att, nb, s.heads, tmax, hd, pos, scale=hd ** -0.5)
+            self._fwd(att.view(nb, tmax, D)[:, pos], nm["proj"] + ".weight", y, bias=pk.wv(nm["proj"] + ".bias"))
+            ops.layernorm_fwd(xin, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, ln, add=y, x_out=xmid)
+            self._fwd(ln, nm["fc1"] + ".weight", h, bias=pk.wv(nm["fc1"] + ".bias"), act=s.act)
+            self._fwd(h, nm["fc2"] + ".weight", y, bias=pk.wv(nm["fc2"] + ".bias"))
+        return xmid, y
+
     # ------------------------------------------------------------------ fp32-accuracy mode (inference)
     def forward_fp32(self, x, nb, ntok):
         """All blocks in fp32 on x fp32 [M, D] (updated in place and returned): LayerNorm -> qkv -> attention -> proj (+x) ->

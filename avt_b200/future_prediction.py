@@ -261,45 +261,55 @@ class AVTh(nn.Module):
         return dfeats
 
     def _run_rollout(self, feats2d, B, T, output_len):
-        """Autoregressive rollout for evaluation (reference :168-202: `output_len` GPT-2 calls, each fed the LAST hidden
-        state of the previous one with `past_key_values` and continuing position ids). Attention is causal and dropout
-        is off in eval mode, so call i of the KV-cached loop equals row T-1+i of ONE causal pass over the T+i embeddings
-        [encoder(feats) ; h_{T-1} ; ... ; h_{T+i-2}] + wpe[0 : T+i]: the rollout is run as output_len growing causal
-        passes over the forward kernels (<= 16 + output_len tokens: the stack is 80-row GEMMs either way), no KV cache to
-        manage. Returns decoded outputs [B, T + output_len - 1, C] (fp32). No autograd graph."""
+        """Autoregressive rollout for evaluation (reference :168-202: `output_len` GPT-2 calls, each after the first fed the
+        LAST hidden state of the previous one with `past_key_values` and continuing position ids). KV-cached: the first call
+        is one causal pass over the T input tokens that keeps every layer's packed qkv rows (they ARE the KV cache); every
+        further call pushes ONE token per clip through the stack (engine.BlockStack.decode_step: M = B rows, the new q/k/v
+        written into the cache, a single-row attention against the cached keys). Returns decoded outputs
+        [B, T + output_len - 1, C] (fp32). No autograd graph, dropout off (eval)."""
         pk, st = self._pack, self._stack
-        C, Dh = self.in_features, self.inter_dim
+        C, Dh, L = self.in_features, self.inter_dim, self.n_layer
         dev = feats2d.device
+        tmax = T + output_len - 1
         pk.refresh_bf16()
         wpe = pk.wv("gpt_model.wpe.weight")
+        # ---- call 0: prefill (the training-mode workspace keeps one qkv buffer per layer; dropout stays off)
+        w = st.workspace(B * T, B, T, True)
         xb = torch.empty(B * T, C, dtype=torch.bfloat16, device=dev)
         ops.cast_bf16(feats2d.contiguous().float(), xb)
-        emb = torch.empty(B * T, Dh, dtype=torch.float32, device=dev)           # encoder(feats) + wpe[:T]
         sk = engine.small_m_split(B * T, Dh, C)
-        ops.gemm(xb, pk.bv("encoder.weight"), emb, pos=wpe[:T], pos_period=T, split_k=sk, workspace=st._gemm_ws(emb, sk))
-        seq = emb.view(B, T, Dh)
-        decoded_all = None
-        for i in range(output_len):
-            Ti = T + i
-            M = B * Ti
-            w = st.workspace(M, B, Ti, False)
-            w["x"][0].copy_(seq.reshape(M, Dh))
-            xmid, y = st.forward(w, B, Ti, False)
-            hid = torch.empty(M, Dh, dtype=torch.float32, device=dev)           # ln_f output, fp32 (fed back below)
-            ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, hid, add=y,
-                              x_out=st._xbuf(w, False, 2 * self.n_layer))
-            hid = hid.view(B, Ti, Dh)
-            new = hid if i == 0 else hid[:, -1:, :]                             # call 0 returns T states, later calls one
-            rows = new.reshape(-1, Dh)
-            hb = torch.empty(rows.shape[0], Dh, dtype=torch.bfloat16, device=dev)
-            ops.cast_bf16(rows.contiguous(), hb)
-            dec = torch.empty(rows.shape[0], C, dtype=torch.float32, device=dev)
-            sk = engine.small_m_split(rows.shape[0], C, Dh)
+        ops.gemm(xb, pk.bv("encoder.weight"), w["x"][0], pos=wpe[:T], pos_period=T, split_k=sk,
+                 workspace=st._gemm_ws(w["x"][0], sk))
+        xmid, y = st.forward(w, B, T, True)
+        hid = torch.empty(B * T, Dh, dtype=torch.float32, device=dev)           # ln_f output, fp32 (fed back below)
+        ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, hid, add=y,
+                          x_out=st._xbuf(w, True, 2 * L))
+
+        def decode(rows32):
+            hb = torch.empty(rows32.shape[0], Dh, dtype=torch.bfloat16, device=dev)
+            ops.cast_bf16(rows32.contiguous(), hb)
+            dec = torch.empty(rows32.shape[0], C, dtype=torch.float32, device=dev)
+            sk = engine.small_m_split(rows32.shape[0], C, Dh)
             ops.gemm(hb, pk.bv("decoder.weight"), dec, split_k=sk, workspace=st._gemm_ws(dec, sk))
-            dec = dec.view(B, -1, C)
-            decoded_all = dec if decoded_all is None else torch.cat([decoded_all, dec], dim=1)
-            if i + 1 < output_len:   # next input embedding: last hidden state + wpe[position T + i]   (:202, position_ids :169-173)
-                seq = torch.cat([seq, hid[:, -1:, :] + wpe[Ti].view(1, 1, Dh)], dim=1)
+            return dec
+
+        decoded_all = decode(hid).view(B, T, C)
+        if output_len == 1:
+            return decoded_all
+        caches = []
+        for l in range(L):                      # KV cache = the prefill's packed qkv rows, padded to tmax positions per clip
+            c = torch.zeros(B * tmax, 3 * Dh, dtype=torch.bfloat16, device=dev)
+            c.view(B, tmax, 3 * Dh)[:, :T].copy_(w["qkv"][l].view(B, T, 3 * Dh))
+            caches.append(c)
+        att = torch.zeros(B * tmax, Dh, dtype=torch.bfloat16, device=dev)
+        last = hid.view(B, T, Dh)[:, -1]
+        for i in range(1, output_len):
+            pos = T + i - 1
+            x = (last + wpe[pos].view(1, Dh)).contiguous()                      # next input: last hidden state + wpe[pos]  (:202, :169-173)
+            xmid, y = st.decode_step(x, caches, att, B, tmax, pos)
+            last = torch.empty(B, Dh, dtype=torch.float32, device=dev)
+            ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, last, add=y)
+            decoded_all = torch.cat([decoded_all, decode(last).view(B, 1, C)], dim=1)
         return decoded_all
 
     # ------------------------------------------------------------------ reference-compatible forward

@@ -256,3 +256,23 @@ def patchify_f32(video, out, patch):
     F, Cc, H, W = video.shape
     assert video.is_contiguous() and video.dtype == out.dtype == torch.float32
     _lib.call("avt_patchify_f32", _ptr(video), _ptr(out), F, Cc, H, W, patch, _stream())
+
+
+def preprocess_u8(frames, out, crop_y, crop_x, *, flip=None, scale=1.0, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    """frames uint8 [F, Hin, Win, 3] (HWC, as decoded) -> out fp32 [F, 3, h, w]: /255, flip (uint8 [F] flags), * scale,
+    normalise, crop - the tail of the reference's transform chain on the GPU (expts/01: mean = std = 0.5)."""
+    _chk_cuda(frames, out, flip)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.shape[-1] == 3 and out.dtype == torch.float32
+    F, Hin, Win, _ = frames.shape
+    assert out.is_contiguous() and out.shape[0] == F and out.shape[1] == 3
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _lib.call("avt_preprocess_u8", _ptr(frames), F, Hin, Win, _ptr(out), out.shape[2], out.shape[3], int(crop_y), int(crop_x),
+              _ptr(flip), float(scale), m3, s3, _stream())
+    return out
+
+
+def attention_simt_decode(qkv_cache, out, B, H, N, hd, q_row, *, scale):
+    """KV-cached decode step: query row q_row of every batch item against keys 0..q_row of the packed qkv cache [B*N, 3*H*hd]."""
+    _chk_cuda(qkv_cache, out)
+    assert qkv_cache.dtype == out.dtype == torch.bfloat16 and qkv_cache.is_contiguous() and out.is_contiguous()
+    _lib.call("avt_attention_simt_decode", _ptr(qkv_cache), _ptr(out), B, H, N, hd, int(q_row), float(scale), _stream())

@@ -189,6 +189,19 @@ int avt_attention_tc_fwd(const void* qkv, void* out, float* lse, int F, int H, i
 int avt_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int F, int H,
                          int N, float scale, void* stream);
 
+/* One KV-cached decode step of the causal attention (evaluation-time rollout, models/future_prediction.py:168-202: HF
+ * GPT2Model called with past_key_values): qkv_cache bf16 [B*N, 3*H*hd] is the packed qkv buffer of the prefill pass with the
+ * new token's q/k/v written into row q_row of every batch item; only that row queries keys 0..q_row. out bf16 [B*N, H*hd]
+ * (row q_row of every item is written). */
+int avt_attention_simt_decode(const void* qkv_cache, void* out, int B, int H, int N, int hd, int q_row, float scale, void* stream);
+
+/* GPU input pipeline: decoded (and resized) uint8 frames [F, Hin, Win, 3] -> normalised fp32 crops [F, 3, h, w], the tail of the
+ * reference's transform chain in one pass: ToTensorVideo, RandomHorizontalFlipVideo (flip[f] != 0; NULL = none), * scale_pix_val,
+ * NormalizeVideo(mean, std), crop at (crop_y, crop_x) (func/train.py:550-584, common/transforms.py:124-191,327-396).
+ * mean3 / std3 are HOST arrays of three floats. The step then copies uint8 frames to the device (4x fewer bytes). */
+int avt_preprocess_u8(const uint8_t* frames, int F, int Hin, int Win, float* out, int h, int w, int crop_y, int crop_x,
+                      const uint8_t* flip, float scale, const float* mean3, const float* std3, void* stream);
+
 /* fp32-accuracy mode (inference; BASELINE.json north star: "within 1e-5 (fp32)"): the same operators on the CUDA cores in
  * fp32, exact erf / tanh GELU. A validation path for the restated arithmetic, not the product path.
  * avt_sgemm_f32: out[m,n] = act(sum_k A[m,k] * Bop[k,n] + bias[n]) + residual[m,n]; B stored [N,K] (b_kn = 0, nn.Linear)

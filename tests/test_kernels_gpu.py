@@ -221,3 +221,25 @@ def test_attention_simt_dropout_consistency():
     assert rel(dqkv, qd.grad) < 4e-3
     keep_rate = mask[torch.tril(torch.ones(N, N, dtype=torch.bool, device="cuda")).expand(B, H, N, N)].mean().item()
     assert abs(keep_rate - (1 - p)) < 0.03
+
+
+@pytest.mark.gpu
+def test_preprocess_u8_matches_reference_transform_chain():
+    """avt_preprocess_u8 vs the reference's transform tail restated with torch ops (common/transforms.py: to_tensor :124-141,
+    hflip :162-170, normalize :144-159, crop :38-44) in the reference's order: ToTensor, flip, * scale, normalize, crop."""
+    from avt_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    F, Hin, Win, h, w = 6, 40, 56, 32, 32
+    frames = torch.randint(0, 256, (F, Hin, Win, 3), dtype=torch.uint8, generator=g)
+    flip = torch.tensor([0, 1, 0, 1, 1, 0], dtype=torch.uint8)
+    mean, std, cy, cx = (0.45, 0.5, 0.4), (0.225, 0.5, 0.25), 5, 17
+    clip = frames.permute(0, 3, 1, 2).float() / 255.0                       # (T, C, H, W)
+    clip = torch.where(flip.bool()[:, None, None, None], clip.flip(-1), clip)
+    clip = (clip * 1.0 - torch.tensor(mean)[None, :, None, None]) / torch.tensor(std)[None, :, None, None]
+    ref = clip[..., cy:cy + h, cx:cx + w]
+    out = torch.empty(F, 3, h, w, device="cuda")
+    ops.preprocess_u8(frames.cuda(), out, cy, cx, flip=flip.cuda(), mean=mean, std=std)
+    assert torch.allclose(out.cpu(), ref, rtol=1e-6, atol=1e-6)
+    out2 = torch.empty(F, 3, Hin, Win, device="cuda")
+    ops.preprocess_u8(frames.cuda(), out2, 0, 0)                             # expts/01: mean = std = 0.5, no flip, no crop
+    assert torch.allclose(out2.cpu(), (frames.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5, rtol=1e-6, atol=1e-6)
