@@ -18,6 +18,8 @@ namespace avt {
 
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                       uint32_t box_outer, int swizzle_bytes);
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer1, uint64_t outer2, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer1, int swizzle_bytes);
 
 constexpr int kTcHd = 64;
 constexpr int kTcKeys = 208;            // MMA N extent / PV contraction length (multiple of 16)
@@ -46,11 +48,11 @@ constexpr int kBwTile = kTcKeys * 128;            // 208 rows x 64 bf16
 constexpr int kBwBlk = 128 * 128;                 // [128 x 64] bf16 block
 constexpr int kBwSmem = 4 * kBwTile + 4 * kBwBlk + 2 * kTcKeys * 4 + 1024 + 128;
 
-#ifdef AVT_ATTN_TRACE
-#define TRACE_DECL __shared__ unsigned long long trace_t[256]; __shared__ int trace_id[256]; __shared__ int trace_n;
-#define TRACE_INIT if (threadIdx.x == 0) trace_n = 0;
-#define TRACE(id) do { if (blockIdx.x == 0) { int i_ = atomicAdd(&trace_n, 1); if (i_ < 256) { trace_t[i_] = global_timer_ns(); trace_id[i_] = (id); } } } while (0)
-#define TRACE_DUMP if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < trace_n && i_ < 256; ++i_) printf("trace %d %llu\n", trace_id[i_], trace_t[i_] - trace_t[0]); }
+#ifdef AVT_ATTN_TRACE   // per-phase timeline of CTA 0: one shared-memory slot per (item < 2, event id): a fire-and-forget clock store
+#define TRACE_DECL __shared__ long long trace_t[512];
+#define TRACE_INIT for (int i_ = threadIdx.x; i_ < 512; i_ += blockDim.x) trace_t[i_] = 0; __syncthreads();
+#define TRACE(id) do { if (blockIdx.x == 0 && n < 2) trace_t[(n & 1) * 256 + (id)] = clock64(); } while (0)
+#define TRACE_DUMP if (blockIdx.x == 0 && threadIdx.x == 0) { long long t0_ = 0; for (int i_ = 0; i_ < 512; ++i_) if (trace_t[i_] && (!t0_ || trace_t[i_] < t0_)) t0_ = trace_t[i_]; for (int i_ = 0; i_ < 512; ++i_) if (trace_t[i_]) printf("btrace %d %d %lld\n", i_ >> 8, i_ & 255, trace_t[i_] - t0_); }
 #else
 #define TRACE_DECL
 #define TRACE_INIT
@@ -92,7 +94,7 @@ constexpr int kB2Smem = 4 * kBwTile + 6 * kBwBlk + 4 * kTcKeys * 4 + 256 + 1024;
 
 __global__ void __launch_bounds__(kB2Threads, 1)
 attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                    const AttnTcBwdParams p, int items) {
+                    const __grid_constant__ CUtensorMap tmDQ, const AttnTcBwdParams p, int items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -121,9 +123,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
   if (warp == kB2Workers) {
     if (lane == 0) {
-      TRACE(0);
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
+      tma_prefetch_desc(&tmDQ);
       mbar_init(bar_tiles, 1);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bar_s[b], 1);
@@ -150,13 +152,24 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   if (warp == kB2Workers) {
     // ------------------------------------------------------------- control warp: one lane issues TMA + MMA
     if (lane == 0) {
+      // The trace of the rolled version (descriptors built from run-time chunk indices) showed the ISSUE of a chunk's 20 MMAs
+      // taking 1800-2300 cycles (85-145 per instruction, tools/ubench_mma.cu: 48 when back to back) - longer than the thread
+      // work of the chunk, with the worker warps idle 40 % of the time. The chunk loop is therefore fully unrolled: a chunk's
+      // buffers depend only on its index within the item (8 chunks per item, so b = lc & 1 and the barrier parities are
+      // compile-time too) and every descriptor is a base built once + an immediate.
       constexpr uint64_t dK_major = smem_desc_sw128(16, 1024);      // K-major operand
       constexpr uint64_t dMN_1blk = smem_desc_sw128(8192, 1024);    // MN-major, one 64-wide block (N = 64)
       constexpr uint64_t dMN_2blk = smem_desc_sw128(kBwBlk, 1024);  // MN-major, two 64-wide blocks 16 KB apart (M = 128)
       constexpr uint32_t idesc_kv = umma_idesc(1, 0, 1, 128, kTcHd);
       constexpr uint32_t idesc_q = umma_idesc(1, 1, 1, 128, kTcHd);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aG = smem_u32(sG), aP = smem_u32(sP),
-                     aS = smem_u32(sS);
+      // base descriptors (start address of the buffer folded in); a byte offset is added as (offset >> 4) - shared-memory
+      // addresses stay below 2^18, so the 14-bit address field never carries
+      const uint64_t kK = smem_desc_addr(dK_major, smem_u32(sK)), kV = smem_desc_addr(dK_major, smem_u32(sV)),
+                     kQ = smem_desc_addr(dK_major, smem_u32(sQ)), kG = smem_desc_addr(dK_major, smem_u32(sG)),
+                     kP = smem_desc_addr(dK_major, smem_u32(sP)), kS = smem_desc_addr(dK_major, smem_u32(sS)),
+                     mG = smem_desc_addr(dMN_1blk, smem_u32(sG)), mQ = smem_desc_addr(dMN_1blk, smem_u32(sQ)),
+                     mK = smem_desc_addr(dMN_1blk, smem_u32(sK)), mS = smem_desc_addr(dMN_2blk, smem_u32(sS));
+      auto off = [](uint64_t d, uint32_t bytes) { return d + uint64_t(bytes >> 4); };
       auto load_tiles = [&](int item) {
         const int f = item / p.H, h = item % p.H;
         mbar_arrive_expect_tx(bar_tiles, 4 * kBwTile);
@@ -165,35 +178,39 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         tma_load_2d(&tmQKV, bar_tiles, sV, 2 * p.D + h * kTcHd, f * N);
         tma_load_2d(&tmDO, bar_tiles, sG, h * kTcHd, f * N);
       };
-      // S^T[b] = K_j Q_c^T, dP^T[b] = V_j dO_c^T for chunk index lc = 4 j + c of the current item
-      auto issue_mma1 = [&](int lc, int b) {
-        const int j = lc >> 2, c = lc & 3;
-        const uint32_t idesc1 = umma_idesc(1, 0, 0, 128, c == 3 ? 16 : 64);
+      // S^T[b] = K_j Q_c^T, dP^T[b] = V_j dO_c^T for chunk index lc = 4 j + c of the current item (b = lc & 1)
+      auto issue_mma1 = [&](const int lc) {
+        const int j = lc >> 2, c = lc & 3, b = lc & 1;
+        const uint32_t idesc1 = c == 3 ? umma_idesc(1, 0, 0, 128, 16) : umma_idesc(1, 0, 0, 128, 64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tm + 128 * b, smem_desc_addr(dK_major, aK + j * kBwBlk + k * 32),
-                   smem_desc_addr(dK_major, aQ + c * 8192 + k * 32), idesc1, k > 0);
+          umma_f16(tm + 128 * b, off(kK, j * kBwBlk + k * 32), off(kQ, c * 8192 + k * 32), idesc1, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tm + 128 * b + 64, smem_desc_addr(dK_major, aV + j * kBwBlk + k * 32),
-                   smem_desc_addr(dK_major, aG + c * 8192 + k * 32), idesc1, k > 0);
+          umma_f16(tm + 128 * b + 64, off(kV, j * kBwBlk + k * 32), off(kG, c * 8192 + k * 32), idesc1, k > 0);
         umma_commit(&bar_s[b]);
       };
-      uint32_t g = 0;      // chunks processed by this CTA so far (8 per item)
       uint32_t n = 0;      // items processed by this CTA so far
       if ((int)blockIdx.x < items) load_tiles(blockIdx.x);
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
         mbar_wait(bar_tiles, n & 1);
-        if (n < 2) TRACE(1);
+        TRACE(1);
         tc_fence_after_sync();
-        issue_mma1(0, g & 1);   // (the buffer was drained: bar_p of chunk g-1 was observed before that chunk's MMA2)
-        for (int lc = 0; lc < 8; ++lc, ++g) {
-          const int j = lc >> 2, c = lc & 3, b = g & 1;
-          const uint32_t ph = (g >> 1) & 1;
-          if (lc < 7) issue_mma1(lc + 1, b ^ 1);     // next chunk's scores run under this chunk's thread work
-          if (n < 2) TRACE(90 + lc);
+        // both score buffers were drained (bar_p of the previous item's last two chunks was observed): chunks 0 and 1
+        issue_mma1(0);
+        issue_mma1(1);
+#pragma unroll
+        for (int lc = 0; lc < 8; ++lc) {
+          const int j = lc >> 2, c = lc & 3, b = lc & 1;
+          const uint32_t ph = (lc >> 1) & 1;          // chunk g = 8 n + lc uses phase (g >> 1) & 1 of its buffer's barriers
+          TRACE(130 + lc);
           mbar_wait(&bar_p[b], ph);                   // P^T / dS^T of this chunk are in smem, S^T/dP^T[b] drained
-          if (n < 2) TRACE(100 + lc);
+          TRACE(100 + lc);
+          tc_fence_after_sync();
+          // The scores of chunk lc + 2 go into the buffer just drained and are issued BEFORE this chunk's dV / dK / dQ MMAs:
+          // the tensor pipe runs in order, and the workers (busy with chunk lc + 1 meanwhile) must never wait for scores.
+          if (lc < 6) issue_mma1(lc + 2);
+          TRACE(90 + lc);
           if (c == 0) {
             const uint32_t v = 2 * n + j;             // dV/dK of the previous key tile must have left TMEM
             if (v > 0) mbar_wait(bar_vkfree, (v - 1) & 1);
@@ -202,26 +219,25 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           tc_fence_after_sync();
           const int ks = c == 3 ? 1 : 4;              // 16-query k-steps in this chunk
           const int sb = (((lc >> 1) & 1) << 1) | (c & 1);   // dS^T block: tile parity x chunk parity
+#pragma unroll
           for (int k = 0; k < ks; ++k) {
-            umma_f16(tm + 256, smem_desc_addr(dK_major, aP + b * kBwBlk + k * 32),
-                     smem_desc_addr(dMN_1blk, aG + c * 8192 + k * 2048), idesc_kv, (c > 0 || k > 0) ? 1u : 0u);
-            umma_f16(tm + 320, smem_desc_addr(dK_major, aS + sb * kBwBlk + k * 32),
-                     smem_desc_addr(dMN_1blk, aQ + c * 8192 + k * 2048), idesc_kv, (c > 0 || k > 0) ? 1u : 0u);
+            umma_f16(tm + 256, off(kP, b * kBwBlk + k * 32), off(mG, c * 8192 + k * 2048), idesc_kv, (c > 0 || k > 0) ? 1u : 0u);
+            umma_f16(tm + 320, off(kS, sb * kBwBlk + k * 32), off(mQ, c * 8192 + k * 2048), idesc_kv, (c > 0 || k > 0) ? 1u : 0u);
           }
           if (c & 1) {   // both halves of query tile t = c/2 are in smem: dQ_t += dS K_j
             const int t = c >> 1;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_f16(tm + 384 + 64 * t, smem_desc_addr(dMN_2blk, aS + (sb & 2) * kBwBlk + k * 2048),
-                       smem_desc_addr(dMN_1blk, aK + j * kBwBlk + k * 2048), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+              umma_f16(tm + 384 + 64 * t, off(mS, (sb & 2) * kBwBlk + k * 2048), off(mK, j * kBwBlk + k * 2048), idesc_q,
+                       (j > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&bar_m2[b]);
-          if (n < 2) TRACE(110 + lc);
+          TRACE(110 + lc);
           if (lc == 7) {
             const int next = item + gridDim.x;
             if (next < items) {
               mbar_wait(&bar_m2[b], ph);   // every MMA of this item retired: the four tiles may be overwritten
-              if (n < 2) TRACE(120);
+              TRACE(120);
               load_tiles(next);
             }
           }
@@ -262,9 +278,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const float2 sl2 = f2(p.scale * 1.4426950408889634f);
     const float2 sc2 = f2(p.scale);
     uint32_t g = 0, n = 0;
+    bool store_pending = false;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
       const int f = item / p.H, h = item % p.H, ip = n & 1;
-      bf16* dbase = p.dqkv + (size_t)f * N * 3 * p.D + h * kTcHd;
       const float* nlse = sNLse + ip * kTcKeys;
       const float* ndel = sNDel + ip * kTcKeys;
       mbar_wait(&bar_dfull[ip], (n >> 1) & 1);
@@ -274,10 +290,15 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int key = j * 128 + kr;
         const bool key_ok = key < N;
         mbar_wait(&bar_s[b], ph);
-        if (threadIdx.x == 0 && n < 2) TRACE(200 + lc);
+        if (threadIdx.x == 0) TRACE(200 + lc);
         if (g >= 2) mbar_wait(&bar_m2[b], ((g - 2) >> 1) & 1);   // chunk g-2's MMAs no longer read sP[b] (nor older dS^T blocks)
-        if (threadIdx.x == 0 && n < 2) TRACE(210 + lc);
+        if (threadIdx.x == 0) TRACE(210 + lc);
         tc_fence_after_sync();
+        if (store_pending) {   // the TMA stores of the last read-out have finished READING their staging blocks
+          if (threadIdx.x == 0) tma_store_wait_read<0>();
+          named_bar_sync(2, 32 * kB2Workers);
+          store_pending = false;
+        }
         const int sb = (((lc >> 1) & 1) << 1) | (c & 1);
         const int nh = c == 3 ? 1 : 2;                          // 16-column halves of this warp's 32 columns (chunk 3: 16 columns, ch 0 only)
         if (c < 3 || ch == 0) {
@@ -319,29 +340,35 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(&bar_p[b]);
-        if (threadIdx.x == 0 && n < 2) TRACE(220 + lc);
+        if (threadIdx.x == 0) TRACE(220 + lc);
         if (c == 3) {
-          // dV_j / dK_j are complete once this chunk's MMAs retire: read them out (32 columns per warp)
+          // dV_j / dK_j are complete once this chunk's MMAs retire: read them out (32 columns per warp). They leave through
+          // swizzled staging tiles + TMA stores (row-per-thread global stores cost one L1 wavefront per row per instruction:
+          // the read-outs of an item took 8 300 of its 29 000 cycles with the whole pipeline drained). Staging = P^T / dS^T
+          // blocks nobody reads any more (every MMA of this key tile retired) and nobody writes before the chunk after next:
+          // dV -> dS^T block 2, dK -> block 3, dQ tile 0 -> dS^T block 1, dQ tile 1 -> P^T block 1. The 3-D tensor map
+          // [frame][token][column] drops rows >= N.
           mbar_wait(&bar_m2[b], ph);
-          if (threadIdx.x == 0 && n < 2) TRACE(230 + lc);
+          if (threadIdx.x == 0) TRACE(230 + lc);
           tc_fence_after_sync();
-          uint32_t a[32], bb[32];
-          tmem_ld_32x32b_x32(t_lane + 256 + 32 * ch, a);
-          tmem_ld_32x32b_x32(t_lane + 320 + 32 * ch, bb);
-          tmem_ld_wait();
-          tc_fence_before_sync();
-          mbar_arrive(bar_vkfree);
-          if (key_ok) {
-            bf16* rk = dbase + (size_t)key * 3 * p.D + p.D + 32 * ch;
-            bf16* rv = rk + p.D;
+          {
+            uint32_t a[32], bb[32];
+            tmem_ld_32x32b_x32(t_lane + 256 + 32 * ch, a);
+            tmem_ld_32x32b_x32(t_lane + 320 + 32 * ch, bb);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            mbar_arrive(bar_vkfree);
+            uint8_t* stv = sS + 2 * kBwBlk + kr * 128;
+            uint8_t* stk = sS + 3 * kBwBlk + kr * 128;
 #pragma unroll
             for (int q2 = 0; q2 < 4; ++q2) {
-              *reinterpret_cast<uint4*>(rv + 8 * q2) = make_uint4(
+              const uint32_t o2 = ((4 * ch + q2) ^ (kr & 7)) << 4;
+              *reinterpret_cast<uint4*>(stv + o2) = make_uint4(
                   pack_bf16x2(__uint_as_float(a[8 * q2]), __uint_as_float(a[8 * q2 + 1])),
                   pack_bf16x2(__uint_as_float(a[8 * q2 + 2]), __uint_as_float(a[8 * q2 + 3])),
                   pack_bf16x2(__uint_as_float(a[8 * q2 + 4]), __uint_as_float(a[8 * q2 + 5])),
                   pack_bf16x2(__uint_as_float(a[8 * q2 + 6]), __uint_as_float(a[8 * q2 + 7])));
-              *reinterpret_cast<uint4*>(rk + 8 * q2) = make_uint4(
+              *reinterpret_cast<uint4*>(stk + o2) = make_uint4(
                   pack_bf16x2(__uint_as_float(bb[8 * q2]), __uint_as_float(bb[8 * q2 + 1])),
                   pack_bf16x2(__uint_as_float(bb[8 * q2 + 2]), __uint_as_float(bb[8 * q2 + 3])),
                   pack_bf16x2(__uint_as_float(bb[8 * q2 + 4]), __uint_as_float(bb[8 * q2 + 5])),
@@ -350,7 +377,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           }
           if (j == 1) {
             // dQ: warp (quarter, ch) reads query tile `ch`, rows quarter*32 + lane, all 64 columns (the last MMA2 retired above)
-            const int q = ch * 128 + kr;
             uint32_t x0[32], x1[32];
             tmem_ld_32x32b_x32(t_lane + 384 + 64 * ch, x0);
             tmem_ld_32x32b_x32(t_lane + 384 + 64 * ch + 32, x1);
@@ -358,26 +384,38 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tc_fence_before_sync();
             mbar_arrive(bar_dqfree);
             mbar_arrive(&bar_dfree[ip]);
-            if (q < N) {
-              bf16* rq = dbase + (size_t)q * 3 * p.D;
+            uint8_t* stq = (ch == 0 ? sS + kBwBlk : sP + kBwBlk) + kr * 128;
 #pragma unroll
-              for (int q2 = 0; q2 < 4; ++q2) {
-                *reinterpret_cast<uint4*>(rq + 8 * q2) = make_uint4(
-                    pack_bf16x2(__uint_as_float(x0[8 * q2]), __uint_as_float(x0[8 * q2 + 1])),
-                    pack_bf16x2(__uint_as_float(x0[8 * q2 + 2]), __uint_as_float(x0[8 * q2 + 3])),
-                    pack_bf16x2(__uint_as_float(x0[8 * q2 + 4]), __uint_as_float(x0[8 * q2 + 5])),
-                    pack_bf16x2(__uint_as_float(x0[8 * q2 + 6]), __uint_as_float(x0[8 * q2 + 7])));
-                *reinterpret_cast<uint4*>(rq + 32 + 8 * q2) = make_uint4(
-                    pack_bf16x2(__uint_as_float(x1[8 * q2]), __uint_as_float(x1[8 * q2 + 1])),
-                    pack_bf16x2(__uint_as_float(x1[8 * q2 + 2]), __uint_as_float(x1[8 * q2 + 3])),
-                    pack_bf16x2(__uint_as_float(x1[8 * q2 + 4]), __uint_as_float(x1[8 * q2 + 5])),
-                    pack_bf16x2(__uint_as_float(x1[8 * q2 + 6]), __uint_as_float(x1[8 * q2 + 7])));
-              }
+            for (int q2 = 0; q2 < 4; ++q2) {
+              *reinterpret_cast<uint4*>(stq + ((q2 ^ (kr & 7)) << 4)) = make_uint4(
+                  pack_bf16x2(__uint_as_float(x0[8 * q2]), __uint_as_float(x0[8 * q2 + 1])),
+                  pack_bf16x2(__uint_as_float(x0[8 * q2 + 2]), __uint_as_float(x0[8 * q2 + 3])),
+                  pack_bf16x2(__uint_as_float(x0[8 * q2 + 4]), __uint_as_float(x0[8 * q2 + 5])),
+                  pack_bf16x2(__uint_as_float(x0[8 * q2 + 6]), __uint_as_float(x0[8 * q2 + 7])));
+              *reinterpret_cast<uint4*>(stq + (((4 + q2) ^ (kr & 7)) << 4)) = make_uint4(
+                  pack_bf16x2(__uint_as_float(x1[8 * q2]), __uint_as_float(x1[8 * q2 + 1])),
+                  pack_bf16x2(__uint_as_float(x1[8 * q2 + 2]), __uint_as_float(x1[8 * q2 + 3])),
+                  pack_bf16x2(__uint_as_float(x1[8 * q2 + 4]), __uint_as_float(x1[8 * q2 + 5])),
+                  pack_bf16x2(__uint_as_float(x1[8 * q2 + 6]), __uint_as_float(x1[8 * q2 + 7])));
             }
           }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 32 * kB2Workers);
+          if (threadIdx.x == 0) {
+            tma_store_3d(&tmDQ, sS + 2 * kBwBlk, 2 * p.D + h * kTcHd, j * 128, f);
+            tma_store_3d(&tmDQ, sS + 3 * kBwBlk, p.D + h * kTcHd, j * 128, f);
+            if (j == 1) {
+              tma_store_3d(&tmDQ, sS + kBwBlk, h * kTcHd, 0, f);
+              tma_store_3d(&tmDQ, sP + kBwBlk, h * kTcHd, 128, f);
+            }
+            tma_store_commit();
+          }
+          store_pending = true;
         }
+        if (threadIdx.x == 0) TRACE(240 + lc);
       }
     }
+    if (threadIdx.x == 0) tma_store_wait<0>();
   }
 
   tc_fence_before_sync();
@@ -395,8 +433,9 @@ extern "C" int avt_attention_tc_bwd(const void* qkv, const void* out, const void
   AVT_REQUIRE(qkv && out && dout && lse && dqkv, "null pointer");
   AVT_REQUIRE(F > 0 && H > 0 && N > 0 && N <= kTcKeys, "tokens per frame must be in [1, 208]");
   const int D = H * kTcHd;
-  CUtensorMap tmQKV, tmDO;
+  CUtensorMap tmQKV, tmDO, tmDQ;
   const uint64_t rows = (uint64_t)F * N;
+  if (int rc = make_tmap_bf16_3d(&tmDQ, dqkv, 3ull * D, (uint64_t)N, (uint64_t)F, 3ull * D, 64, 128, 128)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmQKV, qkv, 3ull * D, rows, 3ull * D, 64, kTcKeys, 128)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmDO, dout, (uint64_t)D, rows, (uint64_t)D, 64, kTcKeys, 128)) return rc;
   AttnTcBwdParams p;
@@ -409,7 +448,7 @@ extern "C" int avt_attention_tc_bwd(const void* qkv, const void* out, const void
     }
     const int items = F * H;
     const int grid = items < num_sms() ? items : num_sms();
-    launch_kernel(attn_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmDO, p, items);
+    launch_kernel(attn_tc_bwd2_kernel, dim3(grid), dim3(kB2Threads), kB2Smem, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmDO, tmDQ, p, items);
     AVT_CUDA_OK(cudaGetLastError());
     return AVT_OK;
 }

@@ -156,8 +156,48 @@ def fc1():
         print(f"{name:28s} {t:7.1f} us {fl / t / 1e6:7.1f} TF/s", flush=True)
 
 
+def vit():
+    """Every GEMM of one ViT-B layer (fwd, dgrad, wgrad) with the epilogue engine.py gives it, at M = 15760 rows."""
+    from avt_b200.engine import _split_k_for
+    M, D = 15760, 768
+    x, att, ln2 = rnd(M, D), rnd(M, D), rnd(M, D)
+    wq, wp, w1, w2 = rnd(3 * D, D, scale=0.03), rnd(D, D, scale=0.03), rnd(4 * D, D, scale=0.03), rnd(D, 4 * D, scale=0.03)
+    bq, bp, b1, b2 = (torch.randn(n, device=dev) for n in (3 * D, D, 4 * D, D))
+    qkv, y, h, z = (torch.empty(M, n, device=dev, dtype=bf) for n in (3 * D, D, 4 * D, 4 * D))
+    dy, dz, dqkv, dln = rnd(M, D), rnd(M, 4 * D), rnd(M, 3 * D), torch.empty(M, D, device=dev, dtype=bf)
+    dz_out = torch.empty(M, 4 * D, device=dev, dtype=bf)
+    gq, gp, g1, g2 = (torch.zeros_like(w, dtype=torch.float32) for w in (wq, wp, w1, w2))
+    gb = torch.zeros(4 * D, device=dev)
+    ops.gemm(ln2, w1, h, bias=b1, act=1, aux_z=z, aux_grad=True)
+
+    def wg(dyv, xv, dW, colsum):
+        sk = _split_k_for(dyv.shape[1], xv.shape[1], M, 256)
+        return lambda: ops.gemm(dyv, xv, dW, a_mn=True, b_mn=True, split_k=sk, accumulate=sk > 1, a_colsum=gb[:dyv.shape[1]] if colsum else None)
+
+    cases = [("fwd qkv", 3 * D * D, lambda: ops.gemm(x, wq, qkv, bias=bq)),
+             ("fwd proj", D * D, lambda: ops.gemm(att, wp, y, bias=bp)),
+             ("fwd fc1 gelu+aux", 4 * D * D, lambda: ops.gemm(ln2, w1, h, bias=b1, act=1, aux_z=z, aux_grad=True)),
+             ("fwd fc2", 4 * D * D, lambda: ops.gemm(h, w2, y, bias=b2)),
+             ("dgrad fc2 *gelu'", 4 * D * D, lambda: ops.gemm(dy, w2, dz_out, b_mn=True, dact_z=z, dact=1, dact_is_grad=True)),
+             ("dgrad fc1", 4 * D * D, lambda: ops.gemm(dz, w1, dln, b_mn=True)),
+             ("dgrad proj", D * D, lambda: ops.gemm(dy, wp, dln, b_mn=True)),
+             ("dgrad qkv", 3 * D * D, lambda: ops.gemm(dqkv, wq, dln, b_mn=True)),
+             ("wgrad fc2", 4 * D * D, wg(dy, h, g2, False)),
+             ("wgrad fc1 +bias", 4 * D * D, wg(dz, ln2, g1, True)),
+             ("wgrad proj", D * D, wg(dy, att, gp, False)),
+             ("wgrad qkv +bias", 3 * D * D, wg(dqkv, x, gq, True))]
+    tot_t = tot_f = 0.0
+    for name, nk, fn in cases:
+        t = timeit(fn)
+        fl = 2.0 * M * nk
+        tot_t += t
+        tot_f += fl
+        print(f"{name:20s} {t:7.1f} us {fl / t / 1e6:7.1f} TF/s", flush=True)
+    print(f"layer total {tot_t:7.1f} us {tot_f / tot_t / 1e6:7.1f} TF/s  (x12 = {12 * tot_t / 1e3:.2f} ms)")
+
+
 if __name__ == "__main__":
-    todo = sys.argv[1:] or ["wgrad", "head", "ln", "attn", "fc1"]
+    todo = sys.argv[1:] or ["wgrad", "head", "ln", "attn", "fc1", "vit"]
     print(torch.cuda.get_device_name(0))
     for name in todo:
         print(f"== {name}")
