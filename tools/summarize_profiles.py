@@ -37,6 +37,49 @@ def launches(src, dst):
     print("wrote", dst)
 
 
+def launches_dram(src, dst, traffic_json=None):
+    """Launch list captured with gpu__time_duration.sum + dram__bytes_read.sum + dram__bytes_write.sum (one CSV row per
+    launch per metric). Also writes profiles/gemm_traffic.json = mean DRAM bytes per ViT GEMM launch, which bench.py
+    reports as roofline.traffic (it cannot measure DRAM traffic itself)."""
+    import json
+    with open(src) as f:
+        rows = list(csv.DictReader(l for l in f if not l.startswith("==")))
+    by_id = collections.OrderedDict()
+    for r in rows:
+        d = by_id.setdefault(int(r["ID"]), {"name": r["Kernel Name"], "grid": r["Grid Size"]})
+        d[r["Metric Name"]] = float(r["Metric Value"])
+    ids = list(by_id)
+    half = [by_id[i] for i in ids[len(ids) // 2:]]          # tools/profile_step.py runs 2 steps: keep the second
+    agg = collections.OrderedDict()
+    for d in half:
+        k = d["name"].split("(")[0].replace("void ", "")
+        a = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[2] += d.get("dram__bytes_read.sum", 0.0)
+        a[3] += d.get("dram__bytes_write.sum", 0.0)
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, "w") as o:
+        o.write(f"# ncu launch list of one training step (second of two): time + DRAM traffic per kernel family, {len(half)} launches, sum {tot/1e6:.3f} ms\n")
+        o.write("# command: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python tools/profile_step.py 2\n")
+        o.write("# (per-launch times are cold-cache and serialised: compare SHARES with the CUDA-graph step bench.py times)\n\n")
+        o.write("| kernel | launches | total us | share | DRAM read MB | DRAM write MB | avg GB/s |\n|---|---:|---:|---:|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            o.write(f"| `{k[:90]}` | {v[0]} | {v[1]/1e3:.1f} | {100*v[1]/tot:.1f}% | {v[2]/1e6:.1f} | {v[3]/1e6:.1f} | {(v[2]+v[3])/max(v[1],1):.0f} |\n")
+        # the big ViT GEMMs: tcgen05 GEMM launches on a full persistent grid (CTA pairs, 148 CTAs)
+        # (the generic-epilogue MN/MN-major instance is left out: those are the AVT-h weight gradients over 80 contraction rows)
+        big = [d for d in half if "gemm_bf16_kernel<256, 2" in d["name"] and "<256, 2, 1, 1, 0>" not in d["name"]]
+        if big:
+            b = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in big) / len(big)
+            t = sum(d.get("gpu__time_duration.sum", 0.0) for d in big)
+            o.write(f"\nViT GEMMs (256-wide CTA-pair launches on the full grid): {len(big)} launches, {t/1e3:.1f} us, mean DRAM traffic {b/1e6:.1f} MB per launch\n")
+            if traffic_json:
+                with open(traffic_json, "w") as j:
+                    json.dump({"bytes_per_launch": b, "launches": len(big), "workload": "cfg2",
+                               "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(big)} ViT GEMM launches of one step ({dst})"}, j, indent=1)
+    print("wrote", dst)
+
+
 def ncu(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -53,4 +96,4 @@ def ncu(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "ncu": ncu}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "launches_dram": launches_dram, "ncu": ncu}[sys.argv[1]](*sys.argv[2:])
