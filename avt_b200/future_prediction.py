@@ -137,6 +137,7 @@ class AVTh(nn.Module):
         self.direct_grads = False
         self._grads_ready_hook = None
         self._before_forward_hook = None   # FlatDataParallel: wait for the all-gather of the sharded-optimizer weights
+        self.bf16_matrix_grads = False     # weight-gradient GEMMs store bf16 (FlatDataParallel + FlatSGD; needs direct_grads)
         self._pack = None
         self._stack = None
         self._rng_dev = None
@@ -167,6 +168,8 @@ class AVTh(nn.Module):
                                 p_attn=self.attn_pdrop, p_resid=self.resid_pdrop, attn_impl="simt")
         self._stack = engine.BlockStack(spec, self._pack)
         self._aux = {}
+        if self.bf16_matrix_grads and self.direct_grads:
+            self._pack.enable_bf16_grads(matrices_direct=True)
         if self.direct_grads:
             self._pack.attach_grads()
 

@@ -104,15 +104,24 @@ def all_gather_shards_(flat, group=None, async_op=False):
 class FlatDataParallel:
     """Wraps an avt_b200.model.AVTModel-like module whose backbone.model / future_predictor own flat buffers."""
 
-    def __init__(self, model, group=None, comm_sms=8, gather_ctas=4):
+    def __init__(self, model, group=None, comm_sms=8, gather_ctas=4, bf16_head_grads=None):
+        """bf16_head_grads: the AVT-h weight-gradient GEMMs store bf16 straight into the payload buffer (what torch autocast
+        produces for a bf16 matmul's weight gradient). Always on for world > 1 (it IS the payload); on a single GPU it is an
+        option (default off) that takes 4 B/parameter out of the weight-gradient stores and the fused SGD's reads."""
         self.model, self.group = model, group
         self.world = _world(group)
+        self.bf16_head_grads = self.world > 1 if bf16_head_grads is None else (bool(bf16_head_grads) or self.world > 1)
         # SMs left to NCCL while collectives overlap the backbone backward / forward (persistent grids shrink)
         self.comm_sms = comm_sms if self.world > 1 else 0
         self.gather_ctas = gather_ctas
         self.vit, self.head = model.backbone.model, model.future_predictor
         self.vit.direct_grads = True
         self.head.direct_grads = True
+        if self.bf16_head_grads:
+            self.head.bf16_matrix_grads = True       # honoured when the head builds its flat buffers (first forward)
+            if self.head._pack is not None and self.head._pack.gb is None:
+                self.head._pack.enable_bf16_grads(matrices_direct=True)
+                self.head._pack.attach_grads()
         self._handles = []          # backbone slices + torch-owned rest
         self._head_rs = None        # (gradient shard, handle) of the AVT-h reduce-scatter (matrix region)
         self._head_small = []       # handles of the all-reduce of the AVT-h vector gradients
@@ -193,9 +202,12 @@ class FlatDataParallel:
 
     def _head_ready(self):
         """AVT-h backward finished (the backbone backward is about to start): reduce-scatter its bf16 gradients."""
-        if self.world == 1:
-            return
         pk = self.head._pack
+        if self.world == 1:
+            if pk.gb is not None:
+                for lo, hi in pk.fp32_grad_ranges():
+                    ops.cast_bf16(pk.g[lo:hi], pk.gb[lo:hi])
+            return
         self._packs_ready()
         for lo, hi in pk.fp32_grad_ranges():        # e.g. the position-embedding gradient, accumulated in fp32
             ops.cast_bf16(pk.g[lo:hi], pk.gb[lo:hi])

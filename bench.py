@@ -192,7 +192,7 @@ def run_ours(args):
     dim = 1024 if "large" in args.model else 768
     model = AVTModel(args.model, dim, NUM_CLASSES).to(dev)
     model.train()
-    dp = FlatDataParallel(model, comm_sms=args.comm_sms)
+    dp = FlatDataParallel(model, comm_sms=args.comm_sms, bf16_head_grads=args.bf16_head_grads)
     video_h, target_h, sub_h = synth_batch(torch, B, T, rank, dev, pin=True)
     video_d, target_d, sub_d = video_h.to(dev), target_h.to(dev), sub_h.to(dev)
 
@@ -385,6 +385,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": workload_config(args, world),
             "notes": {"l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2", "launch": runner["note"],
+                      "grads": "AVT-h weight gradients stored as bf16 by the weight-gradient GEMMs (= the data-parallel payload; "
+                               "what torch autocast yields), everything else fp32" if dp.bf16_head_grads else "fp32",
                       "e2e_input": "pinned host batch -> device staging buffer on a copy stream, overlapped with the previous "
                                    "step (double-buffered prefetch); one H2D copy per step inside the timed region",
                       "roofline_timing": f"per-kernel CUDA events of ONE eager instrumented step ({eager_ms:.2f} ms eager vs "
@@ -457,6 +459,8 @@ def main():
     ap.add_argument("--model", default=None, help="timm model_type (default: the preset's)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python each step")
+    ap.add_argument("--fp32-head-grads", dest="bf16_head_grads", action="store_false",
+                    help="N = 1 only: AVT-h weight gradients in fp32 instead of the bf16 buffer the data-parallel path always uses")
     ap.add_argument("--no-fused-loss-head", dest="fused_loss_head", action="store_false",
                     help="classifier + cross-entropy + accuracy as ~40 eager torch launches (the round-1 path)")
     ap.add_argument("--comm-sms", type=int, default=0,

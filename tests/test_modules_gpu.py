@@ -291,8 +291,10 @@ def test_avth_dropout_train_mode():
     assert rel(acc / 64, e) < 0.25
 
 
-def test_direct_grad_mode_and_fused_sgd_match_torch_sgd():
-    """FlatDataParallel/FlatSGD path (what bench.py runs) == autograd grads + torch.optim.SGD on the same model."""
+@pytest.mark.parametrize("bf16_head_grads", [False, True])
+def test_direct_grad_mode_and_fused_sgd_match_torch_sgd(bf16_head_grads):
+    """FlatDataParallel/FlatSGD path (what bench.py runs) == autograd grads + torch.optim.SGD on the same model.
+    bf16_head_grads: the AVT-h weight-gradient GEMMs store bf16 (single-GPU option; always on under data parallelism)."""
     from avt_b200.model import AVTModel
     from avt_b200.optim import FlatSGD
     from avt_b200.parallel import FlatDataParallel
@@ -309,7 +311,7 @@ def test_direct_grad_mode_and_fused_sgd_match_torch_sgd():
         out, aux = m(video, target_shape=(2,))
         return out["logits/action"].square().mean() + out["past_logits/action"].square().mean() + aux["feat"].mean()
 
-    dp = FlatDataParallel(a)
+    dp = FlatDataParallel(a, bf16_head_grads=bf16_head_grads)
     opt_a = None
     opt_b = torch.optim.SGD(b.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-3)
     for _ in range(3):
@@ -324,10 +326,16 @@ def test_direct_grad_mode_and_fused_sgd_match_torch_sgd():
         opt_b.zero_grad()
         lb.backward()
         opt_b.step()
-        assert abs(la.item() - lb.item()) <= 1e-4 * abs(lb.item()) + 1e-6
+        assert abs(la.item() - lb.item()) <= (3e-3 if bf16_head_grads else 1e-4) * abs(lb.item()) + 1e-6
     pb = dict(b.named_parameters())
     for n, p in a.named_parameters():
-        assert rel(p, pb[n]) < 1e-4, (n, rel(p, pb[n]))
+        # bf16-stored AVT-h matrix gradients: every update carries a 2^-9 relative rounding (the data-parallel payload)
+        tol = 2e-3 if bf16_head_grads else 1e-4
+        assert rel(p, pb[n]) < tol, (n, rel(p, pb[n]))
+    if bf16_head_grads:
+        pk = dp.head._pack
+        assert pk.gb is not None and pk.matrix_grads_bf16
+        assert all(p.grad is None for n, p in dp.head.named_parameters() if p.dim() >= 2)
 
 
 def test_state_dict_load_after_first_forward_updates_kernels():
