@@ -60,6 +60,11 @@ struct GemmCfg {
   static constexpr int smem_bytes(bool staging) {
     return stages(staging) * kStageBytes + (staging ? kStagingBytes : 0) + kBiasBytes + kBarBytes;
   }
+  static constexpr int kDeepStagingBytes = EW * 8 * kSlotBytes;  // 8 slots per epilogue warp (see GemmParams::deep)
+  static constexpr int stages_deep() {
+    const int n = (kSmemLimit - kDeepStagingBytes - kBiasBytes - kBarBytes) / kStageBytes;
+    return n > kMaxStages ? kMaxStages : n;
+  }
   static_assert(stages(true) >= 3, "not enough shared memory for a 3-stage pipeline");
 };
 
@@ -72,6 +77,8 @@ struct GemmParams {
   int stream_k;      // atomics path only: the tiles' k-blocks are dealt out as ONE contiguous range per CTA group
   int stages;        // operand ring depth (GemmCfg::stages)
   int staging;       // TMA staging slots present in shared memory
+  int staging_bytes; // size of the staging area: epilogue warps x slots per warp x kSlotBytes
+  int deep;          // deep store staging (8 slots per warp, no TMA-in slots): GEMMs that are nothing but their epilogue
   int k_rotate;      // producer walks each tile's k-blocks from a tile-dependent start
   float* a_colsum;   // [M] += sum_k A[m, k] (A MN-major only): the bias gradient when A = dY^T of a weight-gradient GEMM
   avt_epilogue_t ep;
@@ -131,6 +138,7 @@ constexpr int kEpiStore = 1;     // [+ bias] -> bf16, TMA store                 
 constexpr int kEpiGeluAux = 2;   // [+ bias], erf-GELU and its derivative -> two bf16 TMA stores (timm Mlp.fc1 forward)
 constexpr int kEpiMulZ = 3;      // x saved gelu' (TMA-loaded) -> bf16, TMA store               (fc2 dgrad through the GELU)
 constexpr int kEpiAtomic = 4;    // fp32 atomics into the output (stream-K weight gradients, both operands MN-major)
+constexpr int kEpiStoreF32 = 5;  // [+ bias] -> fp32, TMA store                              (AVT-h weight gradients, fp32 mode)
 
 template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
@@ -143,7 +151,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nstages = p.stages;
   uint8_t* sStageOut = smem + nstages * Cfg::kStageBytes;                  // [kEpiWarps][2 out + 2 in][kSlotBytes] (if p.staging)
-  float* sBias = reinterpret_cast<float*>(sStageOut + (p.staging ? Cfg::kStagingBytes : 0));  // [2][BN]
+  float* sBias = reinterpret_cast<float*>(sStageOut + p.staging_bytes);  // [2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::kBiasBytes);
   uint64_t* full_bar = bars;                       // [kMaxStages]  TMA -> MMA          (CG=2: the leader's copy is used)
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA          (every CTA's own copy)
@@ -357,8 +365,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool f_dact = kGen ? ep.dact_z != nullptr : EPI == kEpiMulZ;
     const bool f_drop = kGen && ep.drop_p > 0.f;
     const bool f_res = kGen && ep.residual != nullptr;
-    const int f_tma_out = kGen ? p.tma_out : (EPI == kEpiAtomic ? 0 : 1);
-    const bool f_out_fp32 = kGen ? ep.out_fp32 != 0 : EPI == kEpiAtomic;
+    const int f_tma_out = kGen ? p.tma_out : (EPI == kEpiAtomic ? 0 : (EPI == kEpiStoreF32 ? 2 : 1));
+    const bool f_out_fp32 = kGen ? ep.out_fp32 != 0 : (EPI == kEpiAtomic || EPI == kEpiStoreF32);
     const bool f_slices = kGen && p.split_slices != 0;
     const bool f_tma_in = kGen ? p.tma_in != 0 : EPI == kEpiMulZ;
     const int f_act = kGen ? ep.act : (EPI == kEpiGeluAux ? AVT_ACT_GELU_ERF : AVT_ACT_NONE);
@@ -371,8 +379,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int c_part_begin = 32 * (cpart * (kChunks / kParts) + min(cpart, kChunks % kParts));
     const int c_part_end = c_part_begin + 32 * (kChunks / kParts + (cpart < kChunks % kParts ? 1 : 0));
     const int etid = threadIdx.x - 32 * (2 + kSumWarps);
-    uint8_t* out_slots = sStageOut + ew * 4 * kSlotBytes;   // [2] staging for TMA stores
-    uint8_t* in_slots = out_slots + 2 * kSlotBytes;         // [2] staging for TMA loads (dact_z)
+    // [2] staging for TMA stores + [2] for TMA loads (dact_z); deep mode: [8] for stores
+    const bool f_deep = (kGen || EPI == kEpiStore || EPI == kEpiStoreF32) && p.deep != 0;
+    uint8_t* out_slots = sStageOut + ew * (f_deep ? 8 : 4) * kSlotBytes;
+    uint8_t* in_slots = out_slots + 2 * kSlotBytes;
     uint64_t* in_bar = tin_bar + ew * 2;
     uint32_t n_st = 0, n_in_issued = 0, n_in_waited = 0;
     int acc = 0;
@@ -383,9 +393,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool scale_acc = kGen && ep.alpha != 1.0f;
     const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the byte offset (64 B rows)
 
+    // Deep mode (weight gradients over the 80 rows of AVT-h: the kernel is nothing but this epilogue streaming its output):
+    // with two slots per warp, 16 x 2-4 KB in flight per SM, the stores were bound by the TMA round trip (2.9 TB/s); eight
+    // slots per warp (the operand ring needs only 3 stages there) quadruple the bytes in flight.
     auto tma_store_chunk = [&](const CUtensorMap* tm, const float2* v, int col0, int row0) {
-      uint8_t* slot = out_slots + (n_st & 1) * kSlotBytes;
-      if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago no longer reads this slot
+      uint8_t* slot = out_slots + (f_deep ? (n_st & 7) : (n_st & 1)) * kSlotBytes;
+      if (lane == 0) {  // the store that last used this slot no longer reads it
+        if (f_deep) tma_store_wait_read<7>();
+        else tma_store_wait_read<1>();
+      }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -402,9 +418,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // 32 rows x 32 fp32 = 4 KB, 128-byte rows, SWIZZLE_128B (chunk ^= row & 7). Two buffers when the dact_z staging
       // slots are free (both out slots / both in slots): the next chunk is staged while the TMA drains this one - the
       // weight gradients of AVT-h (contraction over 80 rows) are nothing but this epilogue streaming 67 MB to HBM.
-      uint8_t* buf = out_slots + ((!f_tma_in && (n_st & 1)) ? 2 * kSlotBytes : 0);
+      uint8_t* buf = out_slots + (f_deep ? (n_st & 3) * 2 * kSlotBytes : ((!f_tma_in && (n_st & 1)) ? 2 * kSlotBytes : 0));
       if (lane == 0) {
-        if (f_tma_in) tma_store_wait_read<0>();
+        if (f_deep) tma_store_wait_read<3>();
+        else if (f_tma_in) tma_store_wait_read<0>();
         else tma_store_wait_read<1>();
       }
       __syncwarp();
@@ -781,20 +798,31 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t 
   auto kern = gemm_bf16_kernel<BN, CG, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
-    const int mx = Cfg::smem_bytes(true) > Cfg::smem_bytes(false) ? Cfg::smem_bytes(true) : Cfg::smem_bytes(false);
+    int mx = Cfg::smem_bytes(true) > Cfg::smem_bytes(false) ? Cfg::smem_bytes(true) : Cfg::smem_bytes(false);
+    const int deep_bytes = Cfg::stages_deep() * Cfg::kStageBytes + Cfg::kDeepStagingBytes + Cfg::kBiasBytes + Cfg::kBarBytes;
+    if (Cfg::stages_deep() >= 3 && deep_bytes > mx) mx = deep_bytes;
     AVT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     configured = true;
   }
   GemmParams p = p_in;
   p.staging = (p.tma_out || p.tma_in) ? 1 : 0;
   p.stages = Cfg::stages(p.staging != 0);
+  p.staging_bytes = p.staging ? Cfg::kStagingBytes : 0;
+  // deep store staging: generic-epilogue GEMMs with a very short contraction whose output leaves through TMA stores
+  p.deep = ((EPI == kEpiGeneric || EPI == kEpiStore || EPI == kEpiStoreF32) && p.tma_out && !p.tma_in && !p.ep.aux_z &&
+            p.kb_per_split <= 3 && Cfg::stages_deep() >= 3) ? 1 : 0;
+  if (p.deep) {
+    p.stages = Cfg::stages_deep();
+    p.staging_bytes = Cfg::kDeepStagingBytes;
+  }
   const int units = p.num_m_tiles * p.num_n_tiles * (p.stream_k ? p.num_k_blocks : p.split_k);
   const int groups = num_sms() / CG;
   const int grid = CG * (units < groups ? units : groups);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(gemm_threads(EPI));
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(p.staging != 0);
+  cfg.dynamicSmemBytes = p.deep ? p.stages * Cfg::kStageBytes + p.staging_bytes + Cfg::kBiasBytes + Cfg::kBarBytes
+                                : Cfg::smem_bytes(p.staging != 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -923,7 +951,14 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
   if (g_epi_special && cta_group == 2 && block_n == 256 && a_mn && b_mn && p.stream_k && !p.split_slices && e.alpha == 1.0f &&
       !e.bias && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE && e.drop_p == 0.f && !e.residual && e.pos_period == 0)
     epi = kEpiAtomic;
-  if (epi == kEpiAtomic) rc = launch_gemm<256, 2, true, true, kEpiAtomic>(tm, p, s);
+  // weight gradients over a short contraction (AVT-h: 80 rows): the kernel IS its epilogue (67 MB of output per launch), and
+  // the generic body's ~600 instructions per 32-column chunk bounded it at 3.5 TB/s
+  const bool plain_store = g_epi_special && cta_group == 2 && block_n == 256 && a_mn && b_mn && p.split_k == 1 && e.alpha == 1.0f &&
+                           !e.bias && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE && e.drop_p == 0.f && !e.residual &&
+                           e.pos_period == 0 && !a_colsum;
+  if (plain_store && p.tma_out == 1) rc = launch_gemm<256, 2, true, true, kEpiStore>(tm, p, s);
+  else if (plain_store && p.tma_out == 2) rc = launch_gemm<256, 2, true, true, kEpiStoreF32>(tm, p, s);
+  else if (epi == kEpiAtomic) rc = launch_gemm<256, 2, true, true, kEpiAtomic>(tm, p, s);
   else if (epi == kEpiStore) rc = dispatch_epi<kEpiStore>(b_mn, tm, p, s);
   else if (epi == kEpiGeluAux) rc = dispatch_epi<kEpiGeluAux>(b_mn, tm, p, s);
   else if (epi == kEpiMulZ) rc = dispatch_epi<kEpiMulZ>(b_mn, tm, p, s);
