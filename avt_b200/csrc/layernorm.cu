@@ -179,7 +179,8 @@ ln_bwd_pipe_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, 
                    int64_t x_stride, const float* __restrict__ mean, const float* __restrict__ rstd,
                    const float* __restrict__ gamma, int64_t rows, int D, const float* dx_in, float* dx_out,
                    int64_t dx_stride, bf16* __restrict__ dx_bf16, int64_t dxb_stride, int ncols_out /*2 or 3*/,
-                   float* __restrict__ partial /*[grid][ncols_out][D]*/) {
+                   float* __restrict__ partial /*[grid][ncols_out][D]*/, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dcol, int atomic_out) {
   pdl_enter();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,7 +300,10 @@ ln_bwd_pipe_kernel(const void* __restrict__ dy, int dy_fp32, int64_t dy_stride, 
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kLnPipeWarps; ++w) s += red[((size_t)w * 3 + which) * W + c];
-    pout[idx] = s;
+    // accumulate semantics: the CTA's column sums go straight into the (zeroed or running) gradient vectors - 148 atomics per
+    // address instead of a partials buffer + ln_reduce_partials_kernel (38 extra launches per ViT-B step)
+    if (atomic_out) atomicAdd((which == 0 ? dgamma : (which == 1 ? dbeta : dcol)) + c, s);
+    else pout[idx] = s;
   }
 }
 
@@ -516,7 +520,7 @@ template <int VPT>
 static int launch_bwd_pipe(const void* dy, int dy_fp32, int64_t dys, const float* x, int64_t xs, const float* mean,
                            const float* rstd, const float* gamma, int64_t rows, int D, const float* dx_in, float* dx_out,
                            int64_t dxs, bf16* dxb, int64_t dxbs, int ncols_out, float* partial, int blocks, size_t smem,
-                           cudaStream_t st) {
+                           float* dgamma, float* dbeta, float* dcol, int atomic_out, cudaStream_t st) {
   auto kern = ln_bwd_pipe_kernel<VPT>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -524,7 +528,7 @@ static int launch_bwd_pipe(const void* dy, int dy_fp32, int64_t dys, const float
     configured = smem;
   }
   launch_kernel(kern, dim3(blocks), dim3(kLnPipeWarps * 32), smem, st, dy, dy_fp32, dys, x, xs, mean, rstd, gamma, rows, D, dx_in, dx_out, dxs, dxb,
-                                                dxbs, ncols_out, partial);
+                                                dxbs, ncols_out, partial, dgamma, dbeta, dcol, atomic_out);
   AVT_CUDA_OK(cudaGetLastError());
   return AVT_OK;
 }
@@ -606,9 +610,11 @@ extern "C" int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride,
     nparts = num_sms();
     AVT_LN_DISPATCH(D, {
       if (int rc = launch_bwd_pipe<V>(dy, dy_fp32, dy_stride, x, x_stride, mean, rstd, gamma, rows, D, dx_in, dx_out,
-                                      dx_stride, dxb, dxb_stride, ncols_out, partial, nparts, pipe_smem, st))
+                                      dx_stride, dxb, dxb_stride, ncols_out, partial, nparts, pipe_smem, dgamma, dbeta, dx_colsum,
+                                      accumulate ? 1 : 0, st))
         return rc;
     });
+    if (accumulate) return AVT_OK;   // the pipe kernel added its column sums with atomics: no reduction pass
   } else {
     nparts = ln_bwd_blocks(rows);
     ncols_out = 2;

@@ -440,8 +440,9 @@ class BlockStack:
     def backward(self, w, dx, dxb, top_bias_done=False):
         """dx fp32 [M, D] / dxb bf16 copy: gradient w.r.t. the stack output (updated in place to the gradient
         w.r.t. the stack input). Parameter gradients are written into pack.g: matrices are overwritten
-        (or atomically accumulated by split-K units), biases are accumulated by atomics - the caller zeroes
-        the corresponding region of pack.g first (zero_all_grads / zero_small_grads). top_bias_done: the caller's own
+        (or atomically accumulated by split-K units), biases and LayerNorm parameters are accumulated by atomics (the LayerNorm
+        backward adds its column sums straight into them) - the caller zeroes the corresponding region of pack.g first
+        (zero_all_grads / zero_small_grads). top_bias_done: the caller's own
         LayerNorm backward already produced the last layer's fc2 bias gradient (column sums of dx)."""
         s, pk = self.s, self.pack
         M, D = dx.shape
@@ -468,7 +469,7 @@ class BlockStack:
             self._dgrad(w["dz"], nm["fc1"] + ".weight", w["dln"])
             ops.layernorm_bwd(w["dln"], xmid, st[2], st[3], pk.wv(nm["ln2"] + ".weight"), dx,
                               pk.gv(nm["ln2"] + ".weight"), pk.gv(nm["ln2"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb,
-                              dx_colsum=pk.gv(nm["proj"] + ".bias") if fuse_bias else None)
+                              dx_colsum=pk.gv(nm["proj"] + ".bias") if fuse_bias else None, accumulate=True)
             # ---- attention branch: x_mid = x_in + drop(proj(attn(qkv(LN1(x_in)))))
             g = dxb
             if p_res > 0.0:
@@ -482,7 +483,8 @@ class BlockStack:
             self._dgrad(w["dqkv"], nm["qkv"] + ".weight", w["dln"])
             ops.layernorm_bwd(w["dln"], xin, st[0], st[1], pk.wv(nm["ln1"] + ".weight"), dx,
                               pk.gv(nm["ln1"] + ".weight"), pk.gv(nm["ln1"] + ".bias"), w["lnws"], dx_in=dx, dx_bf16=dxb,
-                              dx_colsum=pk.gv(s.names["fc2"].format(i=i - 1) + ".bias") if fuse_bias and i > 0 else None)
+                              dx_colsum=pk.gv(s.names["fc2"].format(i=i - 1) + ".bias") if fuse_bias and i > 0 else None,
+                              accumulate=True)
             if self.layer_done_hook is not None:
                 self.layer_done_hook(i)
         return dx, dxb

@@ -70,6 +70,12 @@ def test_layernorm_fwd_bwd(rows, D, eps):
     dx2 = dres.clone()
     ops.layernorm_bwd(dy.float(), x, mean, rstd, gamma, dx2, dg2, db2, ws, dx_in=dx2, accumulate=True)
     assert rel(dx2, dx) < 1e-6 and rel(dg2, 2 * dg) < 1e-6 and rel(db2, 2 * db) < 1e-6
+    # accumulate mode as the block stack uses it (bf16 dy, column sums of dx too): the pipelined kernel adds its per-CTA
+    # column sums with atomics into the running gradient vectors, no partials pass
+    dg4, db4, dcol4 = dg.clone(), db.clone(), dcol.clone()
+    dx4 = torch.empty(rows, D, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx4, dg4, db4, ws, dx_in=dres, dx_colsum=dcol4, accumulate=True)
+    assert rel(dx4, dx) < 1e-6 and rel(dg4, 2 * dg) < 2e-6 and rel(db4, 2 * db) < 2e-6 and rel(dcol4, 2 * dcol) < 2e-6
     # no residual gradient (first LayerNorm backward of a chain)
     dx3 = torch.empty(rows, D, device="cuda")
     ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx3, dg2, db2, ws)
