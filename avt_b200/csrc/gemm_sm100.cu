@@ -21,6 +21,7 @@
 // wgrad of nn.Linear and HF Conv1D all map onto this one kernel without materialising a transpose. Split-K work
 // units accumulate with fp32 atomics (weight gradients).
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -909,6 +910,16 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
   }
   p.split_slices = 0;
   p.stream_k = (!two_pass && p.split_k > 1) ? 1 : 0;   // fp32 atomics: balance the k-blocks over whatever grid there is
+  {
+    // ... unless uniform split-K units fill one round of the grid almost completely (fc1 / fc2 weight gradients: 36 tiles x 2
+    // = 72 units on 74 CTA pairs). Uniform units walk their k-slabs in lockstep, so the pairs that share an operand block
+    // fetch it at the same time and it comes out of HBM once; stream-K ranges start at unrelated k offsets and ncu saw every
+    // operand byte read twice (243 MB instead of 121 MB, tensor pipe 61 % active against 75 % for the forward GEMM).
+    const int units = p.num_m_tiles * p.num_n_tiles * p.split_k;
+    const int groups = num_sms() / cta_group;
+    static const bool no_uniform = getenv("AVT_WGRAD_STREAMK") != nullptr;
+    if (p.stream_k && !no_uniform && units <= groups && units * 10 >= groups * 9) p.stream_k = 0;
+  }
   if (two_pass && p.split_k > 1) {
     p.split_slices = 1;
     p.ep = avt_epilogue_t{};
@@ -948,7 +959,7 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
   if (simple && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE) epi = kEpiStore;
   else if (simple && e.aux_z && e.aux_mode == 1 && !e.dact_z && e.act == AVT_ACT_GELU_ERF) epi = kEpiGeluAux;
   else if (simple && !e.aux_z && e.dact_z && e.dact_mode == 1 && e.act == AVT_ACT_NONE && !e.bias) epi = kEpiMulZ;
-  if (g_epi_special && cta_group == 2 && block_n == 256 && a_mn && b_mn && p.stream_k && !p.split_slices && e.alpha == 1.0f &&
+  if (g_epi_special && cta_group == 2 && block_n == 256 && a_mn && b_mn && !two_pass && p.split_k > 1 && !p.split_slices && e.alpha == 1.0f &&
       !e.bias && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE && e.drop_p == 0.f && !e.residual && e.pos_period == 0)
     epi = kEpiAtomic;
   // weight gradients over a short contraction (AVT-h: 80 rows): the kernel IS its epilogue (67 MB of output per launch), and
