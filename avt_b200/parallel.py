@@ -146,10 +146,12 @@ class FlatDataParallel:
     # ------------------------------------------------------------------ set-up
     def _packs_ready(self):
         """bf16 gradient buffers (the payload) once the flat buffers exist, i.e. after the first forward."""
-        if self.world > 1 and self.head._pack.gb is None:
-            self.head._pack.enable_bf16_grads(matrices_direct=True)
-            self.head._pack.attach_grads()
-            self.vit._pack.enable_bf16_grads(matrices_direct=False)
+        if self.world > 1:
+            if self.head._pack.gb is None:      # (already there when the head built its buffers with bf16_matrix_grads set)
+                self.head._pack.enable_bf16_grads(matrices_direct=True)
+                self.head._pack.attach_grads()
+            if self.vit._pack.gb is None:
+                self.vit._pack.enable_bf16_grads(matrices_direct=False)
 
     def broadcast_parameters(self):
         """DDP-constructor semantics: every rank starts from rank 0's weights (valid after the first forward)."""
