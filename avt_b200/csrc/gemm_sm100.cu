@@ -140,6 +140,7 @@ constexpr int kEpiGeluAux = 2;   // [+ bias], erf-GELU and its derivative -> two
 constexpr int kEpiMulZ = 3;      // x saved gelu' (TMA-loaded) -> bf16, TMA store               (fc2 dgrad through the GELU)
 constexpr int kEpiAtomic = 4;    // fp32 atomics into the output (stream-K weight gradients, both operands MN-major)
 constexpr int kEpiStoreF32 = 5;  // [+ bias] -> fp32, TMA store                              (AVT-h weight gradients, fp32 mode)
+constexpr int kEpiResidual = 6;  // [+ bias] + fp32 residual (TMA-loaded) -> fp32, TMA store    (proj / fc2 closing a residual branch)
 
 template <int BN, int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
@@ -158,8 +159,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA          (every CTA's own copy)
   uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]        MMA -> epilogue     (every CTA's own copy)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA     (CG=2: the leader's copy)
-  uint64_t* tin_bar = tempty_bar + 2;              // [kEpiWarps][2] TMA -> epilogue warp (dact_z staging)
-  uint64_t* sum_bar = tin_bar + 2 * kEpiWarps;     // [kStages]  MMA -> column-sum warps (stage consumed by the tensor core)
+  uint64_t* tin_bar = tempty_bar + 2;              // [kEpiWarps][4] TMA -> epilogue warp (dact_z: 2 slots, residual: 4)
+  uint64_t* sum_bar = tin_bar + 4 * kEpiWarps;     // [kStages]  MMA -> column-sum warps (stage consumed by the tensor core)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sum_bar + kMaxStages);
   const bool do_colsum = A_MN && p.a_colsum != nullptr;
 
@@ -182,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA in the group
     }
-    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&tin_bar[s], 1);
+    for (int s = 0; s < 4 * kEpiWarps; ++s) mbar_init(&tin_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -366,8 +367,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool f_dact = kGen ? ep.dact_z != nullptr : EPI == kEpiMulZ;
     const bool f_drop = kGen && ep.drop_p > 0.f;
     const bool f_res = kGen && ep.residual != nullptr;
-    const int f_tma_out = kGen ? p.tma_out : (EPI == kEpiAtomic ? 0 : (EPI == kEpiStoreF32 ? 2 : 1));
-    const bool f_out_fp32 = kGen ? ep.out_fp32 != 0 : (EPI == kEpiAtomic || EPI == kEpiStoreF32);
+    const int f_tma_out = kGen ? p.tma_out : (EPI == kEpiAtomic ? 0 : ((EPI == kEpiStoreF32 || EPI == kEpiResidual) ? 2 : 1));
+    const bool f_out_fp32 = kGen ? ep.out_fp32 != 0 : (EPI == kEpiAtomic || EPI == kEpiStoreF32 || EPI == kEpiResidual);
     const bool f_slices = kGen && p.split_slices != 0;
     const bool f_tma_in = kGen ? p.tma_in != 0 : EPI == kEpiMulZ;
     const int f_act = kGen ? ep.act : (EPI == kEpiGeluAux ? AVT_ACT_GELU_ERF : AVT_ACT_NONE);
@@ -382,9 +383,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int etid = threadIdx.x - 32 * (2 + kSumWarps);
     // [2] staging for TMA stores + [2] for TMA loads (dact_z); deep mode: [8] for stores
     const bool f_deep = (kGen || EPI == kEpiStore || EPI == kEpiStoreF32) && p.deep != 0;
-    uint8_t* out_slots = sStageOut + ew * (f_deep ? 8 : 4) * kSlotBytes;
+    uint8_t* out_slots = sStageOut + ew * (EPI == kEpiResidual ? 6 : (f_deep ? 8 : 4)) * kSlotBytes;
     uint8_t* in_slots = out_slots + 2 * kSlotBytes;
-    uint64_t* in_bar = tin_bar + ew * 2;
+    uint64_t* in_bar = tin_bar + ew * 4;
     uint32_t n_st = 0, n_in_issued = 0, n_in_waited = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -463,6 +464,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (ep.bias) {
         for (int i = etid; i < BN; i += 32 * kEpiWarps) bias_s[i] = (n0 + i < p.N) ? __ldg(ep.bias + n0 + i) : 0.f;
       }
+      if constexpr (EPI == kEpiResidual) {
+        // x_out = x_in + (acc + bias): the branch-closing Linear does the residual add itself. The fp32 residual tile arrives by
+        // TMA in 32-row x 16-column boxes (2 KB, 64-byte rows, SWIZZLE_64B) through a ring of FOUR slots per warp: the first
+        // four of a tile's (up to) eight boxes are requested before the accumulator is even complete, so they land under
+        // the main loop; the result leaves the same way through two slots. The extra 8 B per element ride on a tensor-bound
+        // kernel instead of the HBM-bound LayerNorm that used to do the add.
+        const int nhalf = (c_end - c_begin) / 16;
+        auto issue_res = [&](int h) {
+          if (lane == 0) {
+            uint64_t* bar = &in_bar[n_in_issued & 3];
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(bar, kSlotBytes);
+            tma_load_2d(&tmIn, bar, in_slots + (n_in_issued & 3) * kSlotBytes, n0 + c_begin + 16 * h, row0);
+          }
+          ++n_in_issued;
+        };
+        for (int h = 0; h < nhalf && h < 4; ++h) issue_res(h);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int ch0 = c0 + 16 * hh, col0 = n0 + ch0;
+            const uint32_t sl = n_in_waited & 3;
+            mbar_wait(&in_bar[sl], (n_in_waited >> 2) & 1);
+            const uint8_t* islot = in_slots + sl * kSlotBytes + lane * 64;
+            float4 res[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const float4*>(islot + ((j ^ sw) << 4));
+            __syncwarp();
+            ++n_in_waited;
+            const int hnext = (ch0 - c_begin) / 16 + 4;
+            if (hnext < nhalf) issue_res(hnext);                     // into the slot just read
+            uint8_t* oslot = out_slots + (n_st & 1) * kSlotBytes;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ep.bias) b = *reinterpret_cast<const float4*>(bias_s + ch0 + 4 * j);
+              const int i = 16 * hh + 4 * j;
+              *reinterpret_cast<float4*>(oslot + lane * 64 + ((j ^ sw) << 4)) =
+                  make_float4(__uint_as_float(r[i]) + b.x + res[j].x, __uint_as_float(r[i + 1]) + b.y + res[j].y,
+                              __uint_as_float(r[i + 2]) + b.z + res[j].z, __uint_as_float(r[i + 3]) + b.w + res[j].w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmOut, oslot, col0, row0);
+              tma_store_commit();
+            }
+            ++n_st;
+          }
+        }
+      } else {
       if (f_tma_in && c_begin < c_end) issue_in(n0 + c_begin, row0);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -624,6 +686,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      }  // EPI != kEpiResidual
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
@@ -816,14 +879,19 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t 
     p.stages = Cfg::stages_deep();
     p.staging_bytes = Cfg::kDeepStagingBytes;
   }
+  if (EPI == kEpiResidual) {   // 2 out + 4 in slots per epilogue warp: one operand stage less
+    p.staging_bytes = epi_warps(EPI) * 6 * kSlotBytes;
+    const int n = (kSmemLimit - p.staging_bytes - Cfg::kBiasBytes - Cfg::kBarBytes) / Cfg::kStageBytes;
+    p.stages = n > kMaxStages ? kMaxStages : n;
+  }
   const int units = p.num_m_tiles * p.num_n_tiles * (p.stream_k ? p.num_k_blocks : p.split_k);
   const int groups = num_sms() / CG;
   const int grid = CG * (units < groups ? units : groups);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(gemm_threads(EPI));
-  cfg.dynamicSmemBytes = p.deep ? p.stages * Cfg::kStageBytes + p.staging_bytes + Cfg::kBiasBytes + Cfg::kBarBytes
-                                : Cfg::smem_bytes(p.staging != 0);
+  cfg.dynamicSmemBytes = (p.deep || EPI == kEpiResidual) ? p.stages * Cfg::kStageBytes + p.staging_bytes + Cfg::kBiasBytes + Cfg::kBarBytes
+                                                         : Cfg::smem_bytes(p.staging != 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -967,7 +1035,15 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
   const bool plain_store = g_epi_special && cta_group == 2 && block_n == 256 && a_mn && b_mn && p.split_k == 1 && e.alpha == 1.0f &&
                            !e.bias && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE && e.drop_p == 0.f && !e.residual &&
                            e.pos_period == 0 && !a_colsum;
-  if (plain_store && p.tma_out == 1) rc = launch_gemm<256, 2, true, true, kEpiStore>(tm, p, s);
+  // branch-closing Linear with the residual add fused: fp32 residual in / fp32 out through 16-column TMA boxes
+  const bool res_store = g_epi_special && cta_group == 2 && block_n == 256 && !a_mn && p.split_k == 1 && p.tma_out == 2 && e.residual &&
+                         e.alpha == 1.0f && e.pos_period == 0 && e.drop_p == 0.f && !e.aux_z && !e.dact_z && e.act == AVT_ACT_NONE &&
+                         !a_colsum && (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0;
+  if (res_store) {
+    if ((rc = make_tmap_2d(&tm.in, e.residual, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldr, 16, 32, 64, true))) return rc;
+    if ((rc = make_tmap_2d(&tm.out, e.out, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, 16, 32, 64, true))) return rc;
+    rc = dispatch_epi<kEpiResidual>(b_mn, tm, p, s);
+  } else if (plain_store && p.tma_out == 1) rc = launch_gemm<256, 2, true, true, kEpiStore>(tm, p, s);
   else if (plain_store && p.tma_out == 2) rc = launch_gemm<256, 2, true, true, kEpiStoreF32>(tm, p, s);
   else if (epi == kEpiAtomic) rc = launch_gemm<256, 2, true, true, kEpiAtomic>(tm, p, s);
   else if (epi == kEpiStore) rc = dispatch_epi<kEpiStore>(b_mn, tm, p, s);

@@ -34,8 +34,8 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const bf16* __restr
       if (add && c < D) {  // residual stream update fused in: x_new = x + branch (bf16), x_new is what gets normalised
         const uint2 a = *reinterpret_cast<const uint2*>(add + r * add_stride + c);
         v[i].x += bf16_lo(a.x); v[i].y += bf16_hi(a.x); v[i].z += bf16_lo(a.y); v[i].w += bf16_hi(a.y);
-        if (x_out) *reinterpret_cast<float4*>(x_out + r * xo_stride + c) = v[i];
       }
+      if (x_out && c < D) *reinterpret_cast<float4*>(x_out + r * xo_stride + c) = v[i];   // x + add (or a copy of x)
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
     const float mean = warp_sum(s) * inv_d;
@@ -348,8 +348,8 @@ ln_fwd_row_kernel(const float* __restrict__ x, int64_t x_stride, const bf16* __r
       if (add) {
         const uint2 a = *reinterpret_cast<const uint2*>(add + r * add_stride + c);
         v[i].x += bf16_lo(a.x); v[i].y += bf16_hi(a.x); v[i].z += bf16_lo(a.y); v[i].w += bf16_hi(a.y);
-        if (x_out) *reinterpret_cast<float4*>(x_out + r * xo_stride + c) = v[i];
       }
+      if (x_out) *reinterpret_cast<float4*>(x_out + r * xo_stride + c) = v[i];   // x + add, or a compact copy of strided rows
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }

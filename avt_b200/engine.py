@@ -19,6 +19,8 @@ import torch
 from . import ops
 
 _ALIGN = 64  # elements: 256 B in fp32, 128 B in bf16 (TMA needs 16 B; swizzled tiles like 128 B)
+import os as _os
+_FUSE_RESIDUAL = _os.environ.get("AVT_FUSE_RES", "1") != "0"   # A/B switch: 0 = residual adds stay in the LayerNorm kernels
 
 
 class ParamPack:
@@ -325,8 +327,9 @@ class BlockStack:
         return w["x"][max(k, 0)] if train else w["x"][k % 3]
 
     def forward(self, w, nb, ntok, train, rng=(0, 0), dropout=False):
-        """Runs all blocks on w["x"][0]. The last residual add is left pending so the caller can fuse it into its
-        final LayerNorm: returns (x_mid_last fp32, y_last bf16) with stack output = x_mid_last + y_last.
+        """Runs all blocks on w["x"][0]. With residual dropout the last residual add is left pending so the caller can fuse it
+        into its final LayerNorm: returns (x_mid_last fp32, y_last bf16) with stack output = x_mid_last + y_last; without it
+        returns (stack output fp32, None).
         train: keep every layer's activations for backward. dropout: apply spec.p_attn / p_resid."""
         s, pk = self.s, self.pack
         D = s.dim
@@ -336,30 +339,45 @@ class BlockStack:
         p_attn = s.p_attn if dropout else 0.0
         p_res = s.p_resid if dropout else 0.0
         y = w["y"]
+        # Without residual dropout the branch-closing GEMMs (proj, fc2) add the residual themselves and write the fp32 stream
+        # (x_mid = x_in + proj(...), x_next = x_mid + fc2(...)): 8 extra bytes per element on tensor-bound kernels, and the
+        # HBM-bound LayerNorms only read x and write their bf16 output (6 instead of 12 bytes per element).
+        fuse_res = p_res == 0.0
+        fuse_res = fuse_res and _FUSE_RESIDUAL
         for i in range(s.layers):
             j = i if train else 0
             nm = {k: v.format(i=i) for k, v in s.names.items()}
             st = w["st"][j]
             xprev, xin, xmid = (self._xbuf(w, train, 2 * i + k) for k in (-1, 0, 1))
             g1, b1 = pk.wv(nm["ln1"] + ".weight"), pk.wv(nm["ln1"] + ".bias")
-            if i == 0:
+            if i == 0 or fuse_res:     # (fuse_res: the previous layer's fc2 wrote x_in itself)
                 ops.layernorm_fwd(xin, g1, b1, s.eps, w["ln1"][j], st[0], st[1])
             else:   # x_in = x_mid(prev) + mlp branch(prev), fused with this layer's LN1
                 ops.layernorm_fwd(xprev, g1, b1, s.eps, w["ln1"][j], st[0], st[1], add=y, x_out=xin)
             self._fwd(w["ln1"][j], nm["qkv"] + ".weight", w["qkv"][j], bias=pk.wv(nm["qkv"] + ".bias"))
             self._attn_fwd(w["qkv"][j], w["att"][j], w["lse"][j], nb, ntok, hd, scale, p_attn, seed, off + (4 * i << 28),
                            off_dev)
-            self._fwd(w["att"][j], nm["proj"] + ".weight", y, bias=pk.wv(nm["proj"] + ".bias"),
-                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 1) << 28), drop_offset_dev=off_dev)
-            ops.layernorm_fwd(xin, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3],
-                              add=y, x_out=xmid)
+            if fuse_res:
+                self._fwd(w["att"][j], nm["proj"] + ".weight", xmid, bias=pk.wv(nm["proj"] + ".bias"), residual=xin)
+                ops.layernorm_fwd(xmid, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3])
+            else:
+                self._fwd(w["att"][j], nm["proj"] + ".weight", y, bias=pk.wv(nm["proj"] + ".bias"),
+                          drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 1) << 28), drop_offset_dev=off_dev)
+                ops.layernorm_fwd(xin, pk.wv(nm["ln2"] + ".weight"), pk.wv(nm["ln2"] + ".bias"), s.eps, w["ln2"][j], st[2], st[3],
+                                  add=y, x_out=xmid)
             # fc1 epilogue writes gelu(z) and gelu'(z): backward only multiplies
             self._fwd(w["ln2"][j], nm["fc1"] + ".weight", w["h"][j], bias=pk.wv(nm["fc1"] + ".bias"), act=s.act,
                       aux_z=w["z"][j] if train else None, aux_grad=True)
-            self._fwd(w["h"][j], nm["fc2"] + ".weight", y, bias=pk.wv(nm["fc2"] + ".bias"),
-                      drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 2) << 28), drop_offset_dev=off_dev)
+            if fuse_res:
+                self._fwd(w["h"][j], nm["fc2"] + ".weight", self._xbuf(w, train, 2 * i + 2), bias=pk.wv(nm["fc2"] + ".bias"),
+                          residual=xmid)
+            else:
+                self._fwd(w["h"][j], nm["fc2"] + ".weight", y, bias=pk.wv(nm["fc2"] + ".bias"),
+                          drop_p=p_res, drop_seed=seed, drop_offset=off + ((4 * i + 2) << 28), drop_offset_dev=off_dev)
         w["rng"] = (seed, off, off_dev, p_attn, p_res)
         w["dims"] = (nb, ntok)
+        if fuse_res:
+            return self._xbuf(w, train, 2 * s.layers), None      # the stack output itself, nothing pending
         return self._xbuf(w, train, 2 * s.layers - 1), y
 
     def _attn_fwd(self, qkv, out, lse, nb, ntok, hd, scale, p, seed, off, off_dev=None):

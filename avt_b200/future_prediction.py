@@ -214,7 +214,7 @@ class AVTh(nn.Module):
         xmid, y = st.forward(w, B, T, train_graph, rng=(seed, off, off_dev), dropout=drop)
         xf = st._xbuf(w, train_graph, 2 * self.n_layer)
         ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, a["lnf"],
-                          a["fst"][0], a["fst"][1], add=y, x_out=xf)
+                          a["fst"][0], a["fst"][1], add=y, x_out=xf if y is not None else None)   # (y None: xmid IS xf)
         decoded = torch.empty(M, C, dtype=torch.float32, device=dev)
         sk = engine.small_m_split(M, C, Dh)
         ops.gemm(a["lnf"], pk.bv("decoder.weight"), decoded, split_k=sk, workspace=st._gemm_ws(decoded, sk))
@@ -286,7 +286,7 @@ class AVTh(nn.Module):
         xmid, y = st.forward(w, B, T, True)
         hid = torch.empty(B * T, Dh, dtype=torch.float32, device=dev)           # ln_f output, fp32 (fed back below)
         ops.layernorm_fwd(xmid, pk.wv("gpt_model.ln_f.weight"), pk.wv("gpt_model.ln_f.bias"), self.eps, hid, add=y,
-                          x_out=st._xbuf(w, True, 2 * L))
+                          x_out=st._xbuf(w, True, 2 * L) if y is not None else None)
 
         def decode(rows32):
             hb = torch.empty(rows32.shape[0], Dh, dtype=torch.bfloat16, device=dev)

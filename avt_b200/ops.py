@@ -104,7 +104,7 @@ def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, rows=None, x_str
         assert add.dtype == torch.bfloat16
         add_stride = add.stride(0) if add_stride is None else add_stride
     if x_out is not None:
-        assert x_out.dtype == torch.float32 and add is not None
+        assert x_out.dtype == torch.float32      # receives x + add (a plain copy of the normalised rows' input without add)
         x_out_stride = x_out.stride(0) if x_out_stride is None else x_out_stride
     _lib.call("avt_layernorm_fwd", _ptr(x), x_stride, _ptr(add), add_stride or 0, _ptr(x_out), x_out_stride or 0, _ptr(gamma),
               _ptr(beta), float(eps), rows, D, _ptr(y), int(y.dtype == torch.float32), y.stride(0), _ptr(mean), _ptr(rstd),

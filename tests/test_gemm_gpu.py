@@ -277,3 +277,34 @@ def test_gemm_specialized_epilogues_match_generic(kind, b_mn):
     else:
         want = pre
     assert ((outs[0][0].double() - want).abs() <= 2.0**-7 * want.abs() + 1e-3).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b_mn,with_bias", [(False, True), (True, False)])
+def test_gemm_residual_epilogue_matches_generic(b_mn, with_bias):
+    """kEpiResidual (branch-closing Linear: fp32 out = acc + bias + fp32 residual, both through 16-column TMA boxes) against the
+    generic run-time epilogue (bit-identical: the same fp32 additions in the same order) and the fp64 reference."""
+    ops = _ops()
+    from avt_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(43)
+    M, N, K = 1000, 768, 320                     # ragged M (the last pair tile has 232 rows), 3 N tiles, 5 k-blocks
+    a = _mk((M, K), g)
+    b = _mk((K, N) if b_mn else (N, K), g, 0.1)
+    bias = torch.randn(N, generator=g, device="cuda") if with_bias else None
+    res = torch.randn(M, N, generator=g, device="cuda") * 3
+    outs = []
+    for special in (1, 0):
+        _lib.lib().avt_set_gemm_specialized_epilogues(special)
+        out = torch.full((M, N), float("nan"), device="cuda")
+        ops.gemm(a, b, out, b_mn=b_mn, bias=bias, residual=res)
+        outs.append(out)
+    _lib.lib().avt_set_gemm_specialized_epilogues(1)
+    want = _ref(a, b, False, b_mn) + (bias.double() if bias is not None else 0.0) + res.double()
+    assert not torch.isnan(outs[0]).any()
+    rel = lambda x, y: ((x.double() - y).norm() / y.norm()).item()
+    assert rel(outs[0], want) < 1e-5 and rel(outs[1], want) < 1e-5
+    assert (outs[0] - outs[1]).abs().max() <= 1e-5 * want.abs().max()
+    # in place: the residual buffer is also the output (x += branch)
+    x = res.clone()
+    ops.gemm(a, b, x, b_mn=b_mn, bias=bias, residual=x)
+    assert torch.equal(x, outs[0])

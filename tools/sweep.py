@@ -97,6 +97,8 @@ def ln():
         dg, db, dc = (torch.empty(D, device=dev) for _ in range(3))
         ws = torch.empty(ops.layernorm_bwd_workspace(rows, D), dtype=torch.uint8, device=dev)
         ops.layernorm_fwd(x, g, b, 1e-6, y, mean, rstd)
+        tf0 = timeit(lambda: ops.layernorm_fwd(x, g, b, 1e-6, y, mean, rstd))
+        print(f"ln rows {rows} D {D}: fwd without residual add {tf0:6.1f} us {rows * D * 6 / tf0 / 1e3:7.1f} GB/s", flush=True)
         tf = timeit(lambda: ops.layernorm_fwd(x, g, b, 1e-6, y, mean, rstd, add=add, x_out=xo))
         tb = timeit(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dx, dg, db, ws, dx_in=dx, dx_bf16=dxb, dx_colsum=dc))
         fb, bb = rows * D * (4 + 2 + 4 + 2), rows * D * (2 + 4 + 4 + 4 + 2)
@@ -168,6 +170,7 @@ def vit():
     dz_out = torch.empty(M, 4 * D, device=dev, dtype=bf)
     gq, gp, g1, g2 = (torch.zeros_like(w, dtype=torch.float32) for w in (wq, wp, w1, w2))
     gb = torch.zeros(4 * D, device=dev)
+    x32, xo32 = torch.randn(M, D, device=dev), torch.empty(M, D, device=dev)
     ops.gemm(ln2, w1, h, bias=b1, act=1, aux_z=z, aux_grad=True)
 
     def wg(dyv, xv, dW, colsum):
@@ -178,6 +181,8 @@ def vit():
              ("fwd proj", D * D, lambda: ops.gemm(att, wp, y, bias=bp)),
              ("fwd fc1 gelu+aux", 4 * D * D, lambda: ops.gemm(ln2, w1, h, bias=b1, act=1, aux_z=z, aux_grad=True)),
              ("fwd fc2", 4 * D * D, lambda: ops.gemm(h, w2, y, bias=b2)),
+             ("fwd proj +residual f32", D * D, lambda: ops.gemm(att, wp, xo32, bias=bp, residual=x32)),
+             ("fwd fc2 +residual f32", 4 * D * D, lambda: ops.gemm(h, w2, xo32, bias=b2, residual=x32)),
              ("dgrad fc2 *gelu'", 4 * D * D, lambda: ops.gemm(dy, w2, dz_out, b_mn=True, dact_z=z, dact=1, dact_is_grad=True)),
              ("dgrad fc1", 4 * D * D, lambda: ops.gemm(dz, w1, dln, b_mn=True)),
              ("dgrad proj", D * D, lambda: ops.gemm(dy, wp, dln, b_mn=True)),
