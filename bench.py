@@ -367,7 +367,7 @@ def run_ours(args):
     # predecessor's tail, so the sum is a little above what the uninstrumented graph spends in these kernels.) Fallback:
     # one eager instrumented step, whose host enqueue gaps inflate every bracket.
     timing_mode, instr_ms = "eager", None
-    if runner["graph"] is not None:
+    if runner["graph"] is not None and world == 1:   # (N > 1: the eager step below - a second capture would re-capture the collectives)
         try:
             ev_kw["external"] = True
             gi = instrumented(lambda: GraphedStep(core, [video_d, target_d, past_targets(sub_d)], warmup=0))
