@@ -516,11 +516,23 @@ def main():
     args.model = args.model or model
     args.frames = args.frames or frames
     args.batch = args.batch or batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" or (world == 1 and args.cpu_baseline):
+        # The CPU legs are a whole-host baseline. torchrun exports OMP_NUM_THREADS=1, and once the OpenMP / MKL runtimes
+        # have started with that, torch.set_num_threads(n) does not bring the cores back (measured here: a 2048^3 matmul
+        # got SLOWER, 1.17 s vs 0.56 s on one thread vs 0.09 s with 8 real threads) - so the variables are set to the
+        # process's core count BEFORE torch is imported.
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(n)
     if args.impl == "reference":
         run_reference(args)
     else:
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            args.cpu_baseline = args.cpu_baseline and int(os.environ.get("RANK", "0")) == 0
+        if world > 1:
+            args.cpu_baseline = False     # the CPU baseline is an N = 1 leg (on rank 0 of a multi-GPU job the other ranks' host
+                                          # threads would share its cores); `--impl reference` covers every N
         run_ours(args)
 
 
