@@ -75,7 +75,7 @@ SIGNATURES = {
     "avt_attention_tc_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
     "avt_attention_simt_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _u64, _u64, _vp, _vp],
 }
-_SPECIAL = {"avt_abi_version": ([], C.c_int), "avt_last_error": ([], C.c_char_p),
+_SPECIAL = {"avt_abi_version": ([], C.c_int), "avt_last_error": ([], C.c_char_p), "avt_kernel_launch_count": ([], C.c_longlong),
             "avt_layernorm_bwd_workspace_bytes": ([_i64, _i32], C.c_int64)}
 
 
@@ -106,12 +106,12 @@ def check(rc, what=""):
         raise RuntimeError(f"avt_b200 {what} failed (code {rc}): {msg}")
 
 
-# kernels launched per C-ABI call (for bench.py's `gpu_launches` claim)
-_KERNELS_PER_CALL = {"avt_layernorm_bwd": 2, "avt_frame_sum_grads": 2}  # (+1 finishing kernel per two-pass split-K GEMM)
+# kernels launched by the library so far (for bench.py's `gpu_launches` claim): the C side counts every launch it makes
 launch_count = 0
 
 
 def call(name, *args):
     global launch_count
-    check(getattr(lib(), name)(*args), name)
-    launch_count += _KERNELS_PER_CALL.get(name, 1)
+    h = lib()
+    check(getattr(h, name)(*args), name)
+    launch_count = h.avt_kernel_launch_count()

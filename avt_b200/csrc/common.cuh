@@ -44,8 +44,11 @@ __device__ __forceinline__ void pdl_enter() {   // kernels without a prologue wo
   pdl_trigger();
 }
 
+void count_launch();   // core.cu: every kernel launch of the library is counted (avt_kernel_launch_count)
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  count_launch();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -39,9 +39,13 @@ int num_sms_physical() {
   return n;
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }   // (host calls are single-threaded per process)
+
 }  // namespace avt
 
 extern "C" int avt_abi_version(void) { return 1; }
+extern "C" long long avt_kernel_launch_count(void) { return avt::g_launches; }
 extern "C" int avt_set_sm_limit(int n) {
   avt::g_sm_limit = n > 0 ? (n & ~1) : 0;  // even, so CTA pairs still tile the budget
   return AVT_OK;

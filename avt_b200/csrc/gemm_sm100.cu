@@ -75,6 +75,7 @@ struct GemmParams {
   int tma_out;  // `out` (and bf16 aux_z) leave through TMA stores: 1 = bf16 out, 2 = fp32 out (plain overwrite)
   int tma_in;   // dact_z arrives through TMA loads into per-warp staging slots
   int split_slices;  // split-K partials go to out + split*M*ldo (deterministic two-pass) instead of atomics
+  int cluster_reduce;  // split-K units of a tile form ONE thread-block cluster: partials meet through distributed shared memory
   int stream_k;      // atomics path only: the tiles' k-blocks are dealt out as ONE contiguous range per CTA group
   int stages;        // operand ring depth (GemmCfg::stages)
   int staging;       // TMA staging slots present in shared memory
@@ -132,6 +133,83 @@ struct WorkIter {
     return true;
   }
 };
+
+// The run-time epilogue applied to four consecutive columns of one output row (fp32 sums in a4): shared by the finishing pass
+// of the two-pass split-K GEMMs and by the cluster split-K reduction inside the GEMM kernel.
+__device__ __forceinline__ void apply_epilogue4(const avt_epilogue_t& ep, int row, int col, int N, float4 a4, float keep_scale,
+                                                uint64_t drop_off) {
+  float v[4] = {a4.x * ep.alpha, a4.y * ep.alpha, a4.z * ep.alpha, a4.w * ep.alpha};
+  if (ep.bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.pos_period > 0) {
+    const int t = row % ep.pos_period;
+    if (t == 0 && ep.cls) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col));
+      v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.pos + (size_t)t * N + col));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.aux_z) {
+    float a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = ep.aux_mode == 1 ? apply_act_grad(ep.act, v[j]) : v[j];
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col) =
+        make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = apply_act(ep.act, v[j]);
+  if (ep.dact_z) {
+    const uint2 z = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col);
+    const float zz[4] = {bf16_lo(z.x), bf16_hi(z.x), bf16_lo(z.y), bf16_hi(z.y)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= ep.dact_mode == 1 ? zz[j] : apply_act_grad(ep.dact, zz[j]);
+  }
+  if (ep.drop_p > 0.f) {
+    const uint32_t keep = dropout_keep4(ep.drop_seed, drop_off, ((uint64_t)row * (uint64_t)N + (uint64_t)col) >> 2, ep.drop_p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
+  }
+  if (ep.residual) {
+    const float4 b = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col);
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.out_fp32) {
+    float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
+    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    if (ep.accumulate) {
+      const float4 c = *reinterpret_cast<const float4*>(op);
+      o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+    }
+    *reinterpret_cast<float4*>(op) = o;
+  } else {
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo + col) =
+        make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+}
+
+// Finishing pass of a split-K GEMM whose partial sums were written as fp32 slices into `acc`: applies the same
+// epilogue as the fused path. Only used for the weight-streaming M <= 128 GEMMs of AVT-h (80 x N elements) when the
+// split factor does not fit a thread-block cluster.
+__global__ void __launch_bounds__(256)
+epilogue_apply_kernel(const float* __restrict__ acc, int nslices, int M, int N, const avt_epilogue_t ep) {
+  pdl_enter();
+  const int64_t total4 = (int64_t)M * N / 4;
+  const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+  const uint64_t drop_off = ep.drop_offset + ((ep.drop_p > 0.f && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total4; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = g * 4;
+    const int row = (int)(e0 / N), col = (int)(e0 % N);
+    float4 a4 = *reinterpret_cast<const float4*>(acc + e0);
+    for (int sl = 1; sl < nslices; ++sl) {   // fixed summation order: bit-reproducible
+      const float4 b4 = *reinterpret_cast<const float4*>(acc + (size_t)sl * M * N + e0);
+      a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+    }
+    apply_epilogue4(ep, row, col, N, a4, keep_scale, drop_off);
+  }
+}
 
 // Epilogue classes (template parameter EPI)
 constexpr int kEpiGeneric = 0;   // everything avt_epilogue_t can express, decided at run time
@@ -352,6 +430,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   }
+  if constexpr (CG == 1 && EPI == kEpiGeneric) {
+    if (p.cluster_reduce) {   // the epilogue warps' two cluster barriers (partials written / partials consumed)
+      cluster_sync_all();
+      cluster_sync_all();
+    }
+  }
   } else {
     if constexpr (kEpiWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
@@ -449,7 +533,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ++n_in_issued;
     };
 
-    for (WorkIter it(p, group, ngroups); it.next(p, wk);) {
+    bool cluster_done = false;
+    if constexpr (CG == 1 && EPI == kEpiGeneric) {
+      if (p.cluster_reduce) {
+        // Split-K over a thread-block cluster (weight-streaming M <= 128 GEMMs of AVT-h): CTA `split` of the cluster holds the
+        // partial sums of k-slab `split` of ONE output tile. Instead of fp32 slices in HBM + a finishing kernel, every CTA
+        // parks its accumulator in its own (now idle) operand ring, and after a cluster barrier CTA r sums column slice r
+        // of all the peers' copies through distributed shared memory - in a fixed order, so the result is bit-reproducible -
+        // and applies the run-time epilogue to it. One unit per CTA (grid = tiles x split_k).
+        constexpr int PS = BN + 4;                 // padded row pitch (floats): row-per-thread float4 stores stay conflict-free
+        float* P = reinterpret_cast<float*>(smem);
+        const int tile = blockIdx.x / p.split_k;
+        const uint32_t crank = cluster_ctarank();  // == k-slab index (cluster CTAs are consecutive blocks)
+        const int m0 = (tile / p.num_n_tiles) * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int rows_valid = min(kBM, p.M - m0);
+        mbar_wait(&tfull_bar[0], 0);
+        tc_fence_after_sync();
+        const int prow = quarter * 32 + lane;
+        if (quarter * 32 < rows_valid) {
+          const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16);
+#pragma unroll 1
+          for (int c0 = c_part_begin; c0 < c_part_end; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(P + prow * PS + c0 + 4 * j) = make_float4(
+                  __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+        tc_fence_before_sync();
+        cluster_sync_all();                        // every CTA's partial tile is visible cluster-wide
+        {
+          const int cols_per = BN / p.split_k;     // column slice of this CTA (multiple of 4: BN 64 / 128, split 2 / 4 / 8)
+          const int f4_per_row = cols_per / 4;
+          const int total = rows_valid * f4_per_row;
+          const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
+          for (int idx = etid; idx < total; idx += 32 * kEpiWarps) {
+            const int rr = idx / f4_per_row, cc = (int)crank * cols_per + 4 * (idx - rr * f4_per_row);
+            if (n0 + cc >= p.N) continue;
+            const uint32_t addr = smem_u32(P + rr * PS + cc);
+            float4 a4 = ld_shared_cluster_f4(addr, 0);
+            for (int sl = 1; sl < p.split_k; ++sl) {
+              const float4 b4 = ld_shared_cluster_f4(addr, (uint32_t)sl);
+              a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
+            }
+            apply_epilogue4(ep, m0 + rr, n0 + cc, p.N, a4, keep_scale, drop_off);
+          }
+        }
+        cluster_sync_all();                        // nobody leaves while a peer still reads its partial tile
+        cluster_done = true;
+      }
+    }
+    for (WorkIter it(p, group, ngroups); !cluster_done && it.next(p, wk);) {
       const int tile = wk.tile;
       const int split = wk.split;
       const int m0 = (tile / p.num_n_tiles) * (kBM * CG) + (int)rank * kBM;
@@ -708,75 +846,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// Finishing pass of a split-K GEMM whose partial sums were accumulated (fp32 atomics) into `acc`: applies the same
-// epilogue as the fused path. Only used for the weight-streaming M <= 128 GEMMs of AVT-h (80 x N elements).
-__global__ void __launch_bounds__(256)
-epilogue_apply_kernel(const float* __restrict__ acc, int nslices, int M, int N, const avt_epilogue_t ep) {
-  pdl_enter();
-  const int64_t total4 = (int64_t)M * N / 4;
-  const float keep_scale = ep.drop_p > 0.f ? 1.0f / (1.0f - ep.drop_p) : 1.0f;
-  const uint64_t drop_off = ep.drop_offset + ((ep.drop_p > 0.f && ep.drop_offset_dev) ? __ldg(ep.drop_offset_dev) : 0ull);
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total4; g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = g * 4;
-    const int row = (int)(e0 / N), col = (int)(e0 % N);
-    float4 a4 = *reinterpret_cast<const float4*>(acc + e0);
-    for (int sl = 1; sl < nslices; ++sl) {   // fixed summation order: bit-reproducible
-      const float4 b4 = *reinterpret_cast<const float4*>(acc + (size_t)sl * M * N + e0);
-      a4.x += b4.x; a4.y += b4.y; a4.z += b4.z; a4.w += b4.w;
-    }
-    float v[4] = {a4.x * ep.alpha, a4.y * ep.alpha, a4.z * ep.alpha, a4.w * ep.alpha};
-    if (ep.bias) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
-    if (ep.pos_period > 0) {
-      const int t = row % ep.pos_period;
-      if (t == 0 && ep.cls) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.cls + col));
-        v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
-      }
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.pos + (size_t)t * N + col));
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
-    if (ep.aux_z) {
-      float a[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] = ep.aux_mode == 1 ? apply_act_grad(ep.act, v[j]) : v[j];
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux_z) + (size_t)row * ep.ldz + col) =
-          make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = apply_act(ep.act, v[j]);
-    if (ep.dact_z) {
-      const uint2 z = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.dact_z) + (size_t)row * ep.ldz + col);
-      const float zz[4] = {bf16_lo(z.x), bf16_hi(z.x), bf16_lo(z.y), bf16_hi(z.y)};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] *= ep.dact_mode == 1 ? zz[j] : apply_act_grad(ep.dact, zz[j]);
-    }
-    if (ep.drop_p > 0.f) {
-      const uint32_t keep = dropout_keep4(ep.drop_seed, drop_off, (uint64_t)g, ep.drop_p);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * keep_scale : 0.f;
-    }
-    if (ep.residual) {
-      const float4 b = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + col);
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
-    if (ep.out_fp32) {
-      float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col;
-      float4 o = make_float4(v[0], v[1], v[2], v[3]);
-      if (ep.accumulate) {
-        const float4 c = *reinterpret_cast<const float4*>(op);
-        o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-      }
-      *reinterpret_cast<float4*>(op) = o;
-    } else {
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo + col) =
-          make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -886,7 +955,7 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t 
   }
   const int units = p.num_m_tiles * p.num_n_tiles * (p.stream_k ? p.num_k_blocks : p.split_k);
   const int groups = num_sms() / CG;
-  const int grid = CG * (units < groups ? units : groups);
+  const int grid = p.cluster_reduce ? units : CG * (units < groups ? units : groups);   // cluster split-K: one unit per CTA
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(gemm_threads(EPI));
@@ -895,11 +964,12 @@ static int launch_gemm(const GemmMaps& tm, const GemmParams& p_in, cudaStream_t 
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = p.cluster_reduce ? p.split_k : CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  count_launch();
   AVT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, tm.in, p));
   return AVT_OK;
 }
@@ -977,6 +1047,7 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     AVT_CUDA_OK(cudaMemset2DAsync(p.ep.out, (size_t)p.ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s));
   }
   p.split_slices = 0;
+  p.cluster_reduce = 0;
   p.stream_k = (!two_pass && p.split_k > 1) ? 1 : 0;   // fp32 atomics: balance the k-blocks over whatever grid there is
   {
     // ... unless uniform split-K units fill one round of the grid almost completely (fc1 / fc2 weight gradients: 36 tiles x 2
@@ -988,7 +1059,14 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     static const bool no_uniform = getenv("AVT_WGRAD_STREAMK") != nullptr;
     if (p.stream_k && !no_uniform && units <= groups && units * 10 >= groups * 9) p.stream_k = 0;
   }
-  if (two_pass && p.split_k > 1) {
+  // Split factors 2 / 4 / 8 of a single-CTA-tile GEMM run as ONE thread-block cluster per output tile: the partial sums meet in
+  // distributed shared memory inside the kernel (no fp32 slices in HBM, no finishing launch - 52 launches per AVT-h step).
+  static const bool no_cluster = getenv("AVT_NO_CLUSTER_SPLITK") != nullptr;
+  const bool cluster_reduce = two_pass && !no_cluster && cta_group == 1 && !a_colsum &&
+                              (p.split_k == 2 || p.split_k == 4 || p.split_k == 8) && block_n % (4 * p.split_k) == 0;
+  if (cluster_reduce) {
+    p.cluster_reduce = 1;
+  } else if (two_pass && p.split_k > 1) {
     p.split_slices = 1;
     p.ep = avt_epilogue_t{};
     p.ep.alpha = 1.0f;
@@ -997,7 +1075,7 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     p.ep.out_fp32 = 1;
   }
   p.tma_out = p.split_k > 1 ? 0 : (!p.ep.out_fp32 ? 1 : (p.ep.accumulate ? 0 : 2));
-  p.tma_in = p.ep.dact_z ? 1 : 0;
+  p.tma_in = (p.ep.dact_z && !p.cluster_reduce) ? 1 : 0;
 
   GemmMaps tm;
   int rc;
@@ -1059,7 +1137,7 @@ extern "C" int avt_gemm_bf16_colsum(const void* A, int64_t lda, int a_mn, const 
     }
   }
   if (rc) return rc;
-  if (two_pass && p.split_k > 1) {
+  if (two_pass && p.split_k > 1 && !p.cluster_reduce) {
     const int64_t total4 = M * N / 4;
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();

@@ -253,6 +253,18 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// fp32x4 load from the shared memory of CTA `cta` of the cluster, at the address that `local_smem_addr` has in this CTA
+__device__ __forceinline__ float4 ld_shared_cluster_f4(uint32_t local_smem_addr, uint32_t cta) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
+      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(local_smem_addr), "r"(cta)
+      : "memory");
+  return v;
+}
 // Arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(

@@ -25,9 +25,11 @@ def _chk_cuda(*ts):
 
 
 def small_m_block_n(N):
-    """Tile width of the weight-streaming GEMMs (AVT-h, M = B*T <= 128 rows). Measured on B200 (tools/sweep.py head):
-    128-wide tiles (256-byte weight rows per TMA box) + split-K beat 64-wide ones once N >= 2048."""
-    return 128 if N >= 2048 else 64
+    """Tile width of the weight-streaming GEMMs (AVT-h, M = B*T <= 128 rows). Measured on B200 (tools/sweep.py head) with the
+    cluster split-K reduction: N = 2048 outputs run best as 32 tiles of 64 columns x 4 k-slabs (128 CTAs in clusters of 4:
+    8.9 / 17.7 us for K = 2048 / 8192 against 9.7 / 18.5 us with 128-wide tiles), the wide ones (N >= 4096) as 128-wide tiles
+    x 2 k-slabs."""
+    return 128 if N >= 4096 else 64
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, aux_z=None, dact_z=None,
@@ -87,8 +89,6 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT
         assert a_mn and a_colsum.dtype == torch.float32 and a_colsum.numel() == M
         _lib.call("avt_gemm_bf16_colsum", _ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), M, N, K,
                   C.byref(ep), split_k, block_n, cta_group, _ptr(workspace), ws_bytes, _ptr(a_colsum), _stream())
-    if workspace is not None and split_k > 1:
-        _lib.launch_count += 1
     return out
 
 

@@ -105,6 +105,10 @@ int avt_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t l
  * and the parity tests run both). Default 1. */
 int avt_set_gemm_specialized_epilogues(int enable);
 
+/* Number of CUDA kernels this library has launched so far in this process (every launch goes through one helper): what
+ * bench.py reports as `gpu_launches` (delta over the timed region; for a captured graph: launches per replay x replays). */
+long long avt_kernel_launch_count(void);
+
 /* Same GEMM, plus a_colsum[m] += sum_k A[m, k] (fp32 [M], atomics; NULL = off). Requires a_mn = 1. In a weight-gradient
  * GEMM dW = dY^T X the A operand is dY^T, so a_colsum is the bias gradient (column sums of dY): two extra warps add up
  * the A tiles that are in shared memory for the tensor core anyway, and the separate avt_colsum_bf16 pass over

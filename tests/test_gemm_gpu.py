@@ -308,3 +308,52 @@ def test_gemm_residual_epilogue_matches_generic(b_mn, with_bias):
     x = res.clone()
     ops.gemm(a, b, x, b_mn=b_mn, bias=bias, residual=x)
     assert torch.equal(x, outs[0])
+
+
+@pytest.mark.parametrize("N,K,sk,b_mn", [(2048, 2048, 8, True), (8192, 2048, 2, True), (2048, 8192, 8, False), (768, 2048, 8, True),
+                                         (2048, 768, 4, True), (6144, 2048, 4, False)])
+def test_gemm_small_m_cluster_splitk(N, K, sk, b_mn):
+    """AVT-h shapes (M = 80 rows): split factors 2 / 4 / 8 run as one thread-block cluster per output tile and reduce through
+    distributed shared memory inside the kernel. Checked against fp64, against the unsplit kernel, for bit-reproducibility, and
+    with every epilogue the head uses (bias + gelu_new + saved derivative, x saved derivative, fp32 out + residual, dropout)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(N + K + sk)
+    M = 80
+    a = _mk((M, K), g)
+    b = _mk((K, N) if b_mn else (N, K), g, 0.05)
+    bias = torch.randn(N, generator=g, device="cuda")
+    ws = torch.empty(sk * M * N, device="cuda")
+    ref = _ref(a, b, False, b_mn) + bias.double()
+    o1 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    o2, o0 = torch.empty_like(o1), torch.empty_like(o1)
+    ops.gemm(a, b, o1, b_mn=b_mn, bias=bias, split_k=sk, workspace=ws)
+    ops.gemm(a, b, o2, b_mn=b_mn, bias=bias, split_k=sk, workspace=ws)
+    ops.gemm(a, b, o0, b_mn=b_mn, bias=bias)
+    _check(o1, ref, f"cluster split-K {sk}")
+    assert torch.equal(o1, o2)                                   # fixed summation order
+    assert (o1.float() - o0.float()).abs().max() <= 2.0**-7 * ref.abs().max()
+    # gelu_new + saved derivative, then a backward GEMM that multiplies by it
+    h = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, h, b_mn=b_mn, bias=bias, act=2, aux_z=z, aux_grad=True, split_k=sk, workspace=ws)
+    pre = ref.clone().requires_grad_(True)
+    want = _gelu_tanh(pre)
+    (dwant,) = torch.autograd.grad(want.sum(), pre)
+    assert ((h.double() - want.detach()).abs() <= want.detach().abs() * 2.0**-7 + 2e-3).all()
+    assert ((z.double() - dwant).abs() <= dwant.abs() * 2.0**-7 + 2e-3).all()
+    dz = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, dz, b_mn=b_mn, dact_z=z, dact_is_grad=True, split_k=sk, workspace=ws)
+    want2 = _ref(a, b, False, b_mn) * z.double()
+    assert ((dz.double() - want2).abs() <= want2.abs() * 2.0**-7 + 2e-3 * want2.abs().max()).all()
+    # fp32 out + residual; dropout mask identical to the unsplit kernel's (Philox index = element index)
+    res = torch.randn(M, N, generator=g, device="cuda")
+    of = torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, of, b_mn=b_mn, bias=bias, residual=res, split_k=sk, workspace=ws)
+    assert ((of.double() - (ref + res.double())).norm() / (ref + res.double()).norm()).item() < 1e-5
+    d1, d0 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    ops.gemm(a, b, d1, b_mn=b_mn, bias=bias, drop_p=0.25, drop_seed=11, drop_offset=5, split_k=sk, workspace=ws)
+    ops.gemm(a, b, d0, b_mn=b_mn, bias=bias, drop_p=0.25, drop_seed=11, drop_offset=5)
+    assert torch.equal(d1 == 0, d0 == 0)
+    keep = d1 != 0
+    assert 0.70 < keep.float().mean().item() < 0.80
+    assert ((d1.double() - ref / 0.75)[keep].abs().max() / ref.abs().max()).item() < 1e-5
