@@ -59,6 +59,7 @@ SIGNATURES = {
     "avt_layernorm_bwd": [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
                           _vp, _i32, _vp, _i64, _vp],
     "avt_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "avt_zero": [_vp, _i64, _vp],
     "avt_patchify_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "avt_colsum_bf16": [_vp, _i64, _i32, _i64, _vp, _vp],
     "avt_frame_sum_grads": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],

@@ -191,8 +191,8 @@ class VisionTransformer(nn.Module):
         dfeats = dfeats.contiguous().float()
         pk.zero_all_grads()
         dx, dxb = w["dx"], w["dxb"]
-        dx.zero_()
-        dxb.zero_()
+        ops.zero_(dx)
+        ops.zero_(dxb)
         fst = w["aux"]["fstat"]
         # only the CLS rows of dx are non-zero here, so their column sums are the last fc2's bias gradient
         ops.layernorm_bwd(dfeats, xcls, fst[0], fst[1], pk.wv("norm.weight"), dx, pk.gv("norm.weight"), pk.gv("norm.bias"),

@@ -203,6 +203,13 @@ static int grid_for(int64_t work_items, int threads, int per_sm) {
 
 using namespace avt;
 
+extern "C" int avt_zero(void* dst, int64_t bytes, void* stream) {
+  AVT_REQUIRE(dst && bytes >= 0, "null pointer");
+  if (bytes == 0) return AVT_OK;
+  AVT_CUDA_OK(cudaMemsetAsync(dst, 0, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return AVT_OK;
+}
+
 extern "C" int avt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   AVT_REQUIRE(src && dst, "null pointer");
   AVT_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "16-byte alignment");

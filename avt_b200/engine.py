@@ -130,10 +130,10 @@ class ParamPack:
 
     def zero_small_grads(self):
         if self.small_end:
-            self.g[:self.small_end].zero_()
+            ops.zero_(self.g[:self.small_end])
 
     def zero_all_grads(self):
-        self.g.zero_()
+        ops.zero_(self.g)
 
     def attach_grads(self):
         """Direct-gradient mode: make every param.grad a view of the flat gradient buffer (fp32; with bf16 matrix

@@ -134,6 +134,14 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx_out, dgamma, dbeta, workspace, *,
               _stream())
 
 
+def zero_(t):
+    """t[...] = 0 as a stream-ordered memset (contiguous tensors)."""
+    _chk_cuda(t)
+    assert t.is_contiguous()
+    _lib.call("avt_zero", _ptr(t), t.numel() * t.element_size(), _stream())
+    return t
+
+
 def cast_bf16(src, dst):
     _chk_cuda(src, dst)
     assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()

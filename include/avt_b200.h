@@ -147,6 +147,10 @@ int avt_layernorm_bwd(const void* dy, int dy_fp32, int64_t dy_stride, const floa
 /* dst[i] = bf16(src[i]), i < n (weight down-cast of the fp32 master parameters). */
 int avt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* Zero `bytes` bytes at dst (a memset node on the stream / in a captured graph): the flat gradient buffers are zeroed once per
+ * backward because the split-K weight gradients and the bias gradients accumulate with atomics. */
+int avt_zero(void* dst, int64_t bytes, void* stream);
+
 /* Re-tile frames for the patch-embedding GEMM: video fp32 [F, C, H, W] -> out bf16 [F*(P+1), C*ps*ps],
  * P = (H/ps)*(W/ps); row f*(P+1) is zero (CLS slot), row f*(P+1)+1+p is patch p flattened as (c, kh, kw),
  * the K order of Conv2d.weight.view(D, -1). Replaces the im2col inside timm PatchEmbed.proj (Conv2d with
