@@ -49,7 +49,11 @@ def launches_dram(src, dst, traffic_json=None):
         d = by_id.setdefault(int(r["ID"]), {"name": r["Kernel Name"], "grid": r["Grid Size"]})
         d[r["Metric Name"]] = float(r["Metric Value"])
     ids = list(by_id)
-    half = [by_id[i] for i in ids[len(ids) // 2:]]          # tools/profile_step.py runs 2 steps: keep the second
+    # tools/profile_step.py runs 2 steps: keep the last one. A step starts with the patch re-tiling kernel (one launch per
+    # step); halving the list would mis-split, the first step carries one-time launches (weight down-casts, ...)
+    starts = [i for i in ids if "patchify_kernel" in by_id[i]["name"]]
+    first = starts[-1] if starts else ids[len(ids) // 2]
+    half = [by_id[i] for i in ids if i >= first]
     agg = collections.OrderedDict()
     for d in half:
         k = d["name"].split("(")[0].replace("void ", "")
@@ -67,8 +71,9 @@ def launches_dram(src, dst, traffic_json=None):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             o.write(f"| `{k[:90]}` | {v[0]} | {v[1]/1e3:.1f} | {100*v[1]/tot:.1f}% | {v[2]/1e6:.1f} | {v[3]/1e6:.1f} | {(v[2]+v[3])/max(v[1],1):.0f} |\n")
         # the big ViT GEMMs: tcgen05 GEMM launches on a full persistent grid (CTA pairs, 148 CTAs)
-        # (the generic-epilogue MN/MN-major instance is left out: those are the AVT-h weight gradients over 80 contraction rows)
-        big = [d for d in half if "gemm_bf16_kernel<256, 2" in d["name"] and "<256, 2, 1, 1, 0>" not in d["name"]]
+        # (the generic / plain-store MN/MN-major instances are left out: those are the AVT-h weight gradients over 80 contraction rows)
+        big = [d for d in half if "gemm_bf16_kernel<256, 2" in d["name"]
+               and not any(t in d["name"] for t in ("<256, 2, 1, 1, 0>", "<256, 2, 1, 1, 1>", "<256, 2, 1, 1, 5>"))]
         if big:
             b = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in big) / len(big)
             t = sum(d.get("gpu__time_duration.sum", 0.0) for d in big)
