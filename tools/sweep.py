@@ -101,6 +101,8 @@ def ln():
         print(f"ln rows {rows} D {D}: fwd without residual add {tf0:6.1f} us {rows * D * 6 / tf0 / 1e3:7.1f} GB/s", flush=True)
         tf = timeit(lambda: ops.layernorm_fwd(x, g, b, 1e-6, y, mean, rstd, add=add, x_out=xo))
         tb = timeit(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dx, dg, db, ws, dx_in=dx, dx_bf16=dxb, dx_colsum=dc))
+        tba = timeit(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dx, dg, db, ws, dx_in=dx, dx_bf16=dxb, dx_colsum=dc, accumulate=True))
+        print(f"ln rows {rows} D {D}: bwd, accumulate mode (column sums by atomics where the pipelined kernel runs) {tba:6.1f} us", flush=True)
         fb, bb = rows * D * (4 + 2 + 4 + 2), rows * D * (2 + 4 + 4 + 4 + 2)
         print(f"ln rows {rows} D {D}: fwd {tf:6.1f} us {fb / tf / 1e3:7.1f} GB/s | bwd(+reduce) {tb:6.1f} us {bb / tb / 1e3:7.1f} GB/s",
               flush=True)
