@@ -1,14 +1,8 @@
-// ViT spatial attention on tcgen05 tensor cores: softmax(Q K^T * scale) V for N <= 208 tokens, head_dim 64.
-//
-// One CTA per (frame, head). The whole key range fits one MMA N extent (208 = 13*16 >= 197), so there is
-// no online-softmax rescaling: S = Q K^T lands in TMEM in one shot, each softmax thread owns one query row
-// (TMEM lane) and needs no shuffles, P is written as bf16 into 128B-swizzled smem (K-major A operand),
-// O = P V accumulates in TMEM over the dead S columns.
-//   warps 0-3 : softmax + epilogue for query rows   0..127 (TMEM lanes = rows, S at columns   0..207)
-//   warps 4-7 : softmax + epilogue for query rows 128..255 (                   S at columns 256..463)
-//   warp  8   : TMA loads (Q tiles, K, V straight out of the packed qkv matrix) and all tcgen05.mma issue
-// Layout: qkv bf16 [F*N, 3*D], column = s*D + h*64 + d (timm Attention.qkv packing); out bf16 [F*N, D].
-// Replaces timm Attention.forward: q@k^T*scale -> softmax -> attn@v (4 kernels + 80*12*197^2 score tensor).
+// ViT spatial attention BACKWARD on tcgen05 tensor cores (N <= 208 tokens, head_dim 64); the forward kernel lives in
+// attention_fwd.cu. Layout: qkv / dqkv bf16 [F*N, 3*D], column = s*D + h*64 + d (timm Attention.qkv packing); out, dout bf16
+// [F*N, D]; lse fp32 [F*H, N] (log-sum-exp of the scaled scores, saved by the forward). Replaces the autograd backward of timm
+// Attention.forward (q@k^T*scale -> softmax -> attn@v; models/video_classification.py:255-256 runs timm's ViT per frame)
+// without ever materialising the 80*12*197^2 score / probability tensors.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
@@ -23,13 +17,6 @@ int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 
 constexpr int kTcHd = 64;
 constexpr int kTcKeys = 208;            // MMA N extent / PV contraction length (multiple of 16)
-constexpr int kTcQBytes = 128 * 128;    // one Q tile: 128 rows x 64 bf16
-constexpr int kTcKVBytes = kTcKeys * 128;
-constexpr int kTcPBlk = 128 * 128;      // one P block: 128 rows x 64 keys bf16
-constexpr int kTcPBytes = 4 * kTcPBlk;  // keys padded to 256 in smem addressing (only 208 are read)
-constexpr int kTcSmem = 2 * kTcQBytes + 2 * kTcKVBytes + 2 * kTcPBytes + 256;
-constexpr int kTcThreads = 288;
-
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -69,25 +56,27 @@ struct AttnTcBwdParams {
   float scale;
 };
 
-// ------------------------------------------------------------------------------------------------ backward, v2
-// Persistent and software-pipelined. The v1 timeline (TRACE, one CTA = one (frame, head)): 4.7 us prologue (tile loads,
-// delta), then per 128-query iteration  threads 1.0-1.3 us -> MMA 1.6-2.9 us -> threads ...  strictly in series
-// (S^T/dP^T single-buffered in TMEM), 2.2 us read-out: 20.6 us per item, 7 rounds of CTAs per layer.
-// v2:
+// ------------------------------------------------------------------------------------------------ the kernel
+// Persistent and software-pipelined (v1, one CTA per (frame, head) with threads -> MMA -> threads strictly in series, took
+// 144 us per layer at 80 x 12 x 197):
 //   * one CTA per SM walks items (frame, head) = blockIdx.x, +gridDim.x, ...; TMEM / barriers are set up once;
-//   * queries are processed in chunks of 64 columns and S^T / dP^T are double-buffered in TMEM (2 x 128 columns), so the
-//     tensor core computes chunk g+1's scores while the threads turn chunk g into P^T / dS^T, and chunk g's
-//     dV / dK / dQ MMAs run under chunk g+1's thread work;
+//   * queries are processed in chunks of 64 columns and S^T / dP^T are double-buffered in TMEM (2 x 128 columns): the
+//     tensor core computes the scores of chunk lc+2 while the workers turn chunk lc+1 into P^T / dS^T, and chunk lc's
+//     dV / dK / dQ MMAs are issued behind them (the pipe runs in order: the workers never wait for scores);
 //   * P^T ping-pongs between 2 smem blocks, dS^T between 4 (the dQ MMA of a 128-query tile reads two of them);
+//   * the issuing thread's chunk loop is fully unrolled: a chunk's buffers depend only on its index within the item, so
+//     every operand descriptor is a base built once + an immediate (from run-time indices the ISSUE of a chunk's 20 MMAs
+//     took 1800-2300 cycles, longer than the thread work of the chunk);
 //   * delta = rowsum(dO o O) and lse*log2(e) of the NEXT item are prepared by two otherwise idle warps;
-//   * the read-out of dK / dV / dQ overlaps the TMA loads of the next item's tiles.
+//   * dK / dV / dQ leave through swizzled staging tiles (P^T / dS^T blocks that are dead at that point) + TMA stores
+//     whose 3-D map drops rows >= N; the tiles arrive through 3-D maps too (rows >= N zero-filled).
 // TMEM columns: S^T[b] 128b..+63 | dP^T[b] 128b+64..+127 (b = 0,1) | dV 256 | dK 320 | dQ tile0 384 | dQ tile1 448.
-// Measured (TRACE, B200): 113 us/layer vs 144 us for v1. What bounds it now: (1) the small MMAs are operand-fetch
-// bound, not math bound - a K-major SW128 operand serves one 16-element k-step as 32 bytes out of every 128-byte row,
-// so a 128 x 64 x 16 MMA (32 math cycles) spends ~130-190 cycles pulling 128 + 64 smem lines (interleaving independent
-// accumulator chains did not help: 120 us); (2) the worker warps are bound by the TMEM read port (64 B/clk/SM):
-// S^T + dP^T are 64 KB per chunk = ~0.55 us. Next step: 32-byte-slab (SWIZZLE_32B) operand tiles and P^T / dS^T as
-// TMEM A operands, which cut the operand fetch per k-step to a quarter.
+// Measured (B200, phase trace AVT_ATTN_TRACE + ncu, profiles/r02_attn_ncu.txt): 100 us per layer, ~20 000 cycles per item.
+// What bounds it: the 8 worker warps execute ~250 dependent instructions per chunk at ~0.12 IPC each (removing the
+// exponentials, the TMEM loads, the proxy fences or the 256-thread barrier arrivals one at a time changes nothing; the
+// broadcast ld.shared of lse / delta is worth 6 us), and the 148 small MMAs of an item take ~75 cycles each in situ
+// (tools/ubench_mma.cu: 48 back to back, whatever N <= 64). Tried and dropped: k-steps spread over lanes with per-lane
+// commits (130 us), 16 worker warps (109 us), one batched 32-column TMEM load per array (no change).
 constexpr int kB2Workers = 8;                      // worker warps (2 per TMEM lane quarter)
 constexpr int kB2Threads = 32 * (kB2Workers + 3);  // + control warp + 2 delta warps
 constexpr int kB2Smem = 4 * kBwTile + 6 * kBwBlk + 4 * kTcKeys * 4 + 256 + 1024;
