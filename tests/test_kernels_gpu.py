@@ -249,3 +249,19 @@ def test_preprocess_u8_matches_reference_transform_chain():
     out2 = torch.empty(F, 3, Hin, Win, device="cuda")
     ops.preprocess_u8(frames.cuda(), out2, 0, 0)                             # expts/01: mean = std = 0.5, no flip, no crop
     assert torch.allclose(out2.cpu(), (frames.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5, rtol=1e-6, atol=1e-6)
+
+
+def test_zero_and_launch_counter():
+    """avt_zero (memset node behind the gradient-buffer zeroing) and avt_kernel_launch_count (bench.py's gpu_launches)."""
+    ops = _ops()
+    from avt_b200 import _lib
+    t = torch.randn(1000, 77, device="cuda")
+    ops.zero_(t[:500])
+    assert t[:500].abs().max().item() == 0.0 and t[500:].abs().min().item() > 0.0
+    n0 = _lib.lib().avt_kernel_launch_count()
+    a = torch.randn(64, 128, device="cuda")
+    b = torch.empty(64, 128, device="cuda", dtype=torch.bfloat16)
+    ops.cast_bf16(a, b)
+    ops.cast_bf16(a, b)
+    assert _lib.lib().avt_kernel_launch_count() - n0 == 2       # memsets are not kernels; every kernel launch is counted
+    assert _lib.launch_count == _lib.lib().avt_kernel_launch_count()
