@@ -80,8 +80,11 @@ def launches_dram(src, dst, traffic_json=None):
             o.write(f"\nViT GEMMs (256-wide CTA-pair launches on the full grid): {len(big)} launches, {t/1e3:.1f} us, mean DRAM traffic {b/1e6:.1f} MB per launch\n")
             if traffic_json:
                 with open(traffic_json, "w") as j:
-                    json.dump({"bytes_per_launch": b, "launches": len(big), "workload": "cfg2",
-                               "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(big)} ViT GEMM launches of one step ({dst})"}, j, indent=1)
+                    # keyed by "<model>:<frames>:<clips per GPU>" (bench.py looks its own workload up); profile_step.py runs cfg2
+                    json.dump({"vit_base_patch16_224:10:8": {
+                        "bytes_per_launch": b, "launches": len(big), "workload": "cfg2",
+                        "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(big)} ViT GEMM launches of one step ({dst})"}},
+                        j, indent=1)
     print("wrote", dst)
 
 
