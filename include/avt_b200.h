@@ -58,11 +58,16 @@ int avt_set_pdl(int enable);
  *                draws a fresh mask on every replay)
  *   if residual: v += residual[r * ldr + c]
  *   out[r * ldo + c] = out_fp32 ? v : bf16(v)
- * With split_k > 1 the partial sums are combined with fp32 atomics: directly into `out` when the epilogue is a plain
- * fp32 output (weight gradients; zero-filled first unless `accumulate` is set), otherwise into the
- * caller's split_k*M*N fp32 `workspace` (one slice per split, plain stores, summed in a fixed order: bit-reproducible),
- * followed by a small finishing kernel that applies the epilogue (used for the
- * weight-streaming M <= 128 GEMMs of AVT-h, where one tile per CTA would leave most SMs idle). */
+ * With split_k > 1 the partial sums are combined
+ *  - with fp32 atomics directly into `out` when the epilogue is a plain fp32 output and no workspace is given (weight
+ *    gradients; zero-filled first unless `accumulate` is set). The k-range is cut uniformly when tiles x split_k fill one
+ *    round of the grid, otherwise into one contiguous tiles x k-blocks range per CTA pair (stream-K);
+ *  - otherwise (fused epilogue; the weight-streaming M <= 128 GEMMs of AVT-h, where one tile per CTA would leave most SMs
+ *    idle; the caller passes a split_k*M*N fp32 `workspace`): split factors 2 / 4 / 8 of single-CTA tiles run as ONE
+ *    thread-block cluster per output tile and reduce through distributed shared memory inside the kernel, the epilogue
+ *    applied in place (fixed summation order: bit-reproducible; the workspace stays untouched); any other factor
+ *    writes one fp32 slice per split into the workspace and a small finishing kernel sums them and applies the
+ *    epilogue. */
 typedef struct avt_epilogue {
   const float* bias;
   const float* residual;
