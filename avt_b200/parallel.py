@@ -104,7 +104,7 @@ def all_gather_shards_(flat, group=None, async_op=False):
 class FlatDataParallel:
     """Wraps an avt_b200.model.AVTModel-like module whose backbone.model / future_predictor own flat buffers."""
 
-    def __init__(self, model, group=None, comm_sms=12, gather_ctas=4, bf16_head_grads=None):
+    def __init__(self, model, group=None, comm_sms=12, gather_ctas=16, bf16_head_grads=None):
         """bf16_head_grads: the AVT-h weight-gradient GEMMs store bf16 straight into the payload buffer (what torch autocast
         produces for a bf16 matmul's weight gradient). Always on for world > 1 (it IS the payload); on a single GPU it is an
         option (default off) that takes 4 B/parameter out of the weight-gradient stores and the fused SGD's reads."""

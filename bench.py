@@ -192,7 +192,7 @@ def run_ours(args):
     dim = 1024 if "large" in args.model else 768
     model = AVTModel(args.model, dim, NUM_CLASSES).to(dev)
     model.train()
-    dp = FlatDataParallel(model, comm_sms=args.comm_sms, bf16_head_grads=args.bf16_head_grads)
+    dp = FlatDataParallel(model, comm_sms=args.comm_sms, gather_ctas=args.gather_ctas, bf16_head_grads=args.bf16_head_grads)
     video_h, target_h, sub_h = synth_batch(torch, B, T, rank, dev, pin=True)
     video_d, target_d, sub_d = video_h.to(dev), target_h.to(dev), sub_h.to(dev)
 
@@ -523,6 +523,10 @@ def main():
                     help="N = 1 only: AVT-h weight gradients in fp32 instead of the bf16 buffer the data-parallel path always uses")
     ap.add_argument("--no-fused-loss-head", dest="fused_loss_head", action="store_false",
                     help="classifier + cross-entropy + accuracy as ~40 eager torch launches (the round-1 path)")
+    ap.add_argument("--gather-ctas", type=int, default=16,
+                    help="CTAs of the communicator that all-gathers the sharded AVT-h bf16 weights under the backbone forward "
+                         "(measured ms/step, cfg2, N = 2: 4 -> 14.61, 8 -> 14.46, 16 -> 14.12, 24 -> 14.38, 32 -> 14.74; "
+                         "N = 8: 4 -> 14.79, 16 -> 14.45)")
     ap.add_argument("--comm-sms", type=int, default=0,
                     help="SMs left to NCCL while the bf16 gradient collectives overlap the backbone backward (0 = auto: 12; the "
                          "AVT-h reduce-scatter has the whole 8 ms backward for 0.6 GB, the per-layer backbone all-reduces are "
