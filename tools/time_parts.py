@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(42)
 B, T = 8, 10
 model = AVTModel().to(dev).train()
-dp = FlatDataParallel(model)
+dp = FlatDataParallel(model, bf16_head_grads=True)     # as bench.py runs it
 video, target, sub = (t.to(dev) for t in bench.synth_batch(torch, B, T, 0, dev))
 ptgt = past_targets(sub)
 

@@ -25,7 +25,7 @@ model_type = sys.argv[3] if len(sys.argv) > 3 else "vit_base_patch16_224"
 torch.manual_seed(42)
 dev = torch.device("cuda", 0)
 model = AVTModel(model_type, 1024 if "large" in model_type else 768, bench.NUM_CLASSES).to(dev).train()
-dp = FlatDataParallel(model)
+dp = FlatDataParallel(model, bf16_head_grads=True)
 video, target, sub = (t.to(dev) for t in bench.synth_batch(torch, B, T, 0, dev))
 state = {"opt": None}
 
@@ -67,7 +67,7 @@ def traced(name, *args):
     orig_call(name, *args)
     b.record()
     key = name
-    if name == "avt_gemm_bf16":
+    if name.startswith("avt_gemm_bf16"):
         M, N, K = (int(getattr(v, "value", v)) for v in args[6:9])
         key = f"gemm M{M} N{N} K{K} a{args[2]}b{args[5]} sk{args[10]}"
     elif name.startswith("avt_layernorm"):
