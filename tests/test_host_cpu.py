@@ -258,3 +258,44 @@ def test_reduce_scatter_update_all_gather_gloo_world2():
     assert res[0][:4] == (0, (0, 512), True, [1.5]) and res[1][:4] == (1, (512, 1024), True, [1.5])
     for r in res:     # every rank ends with both shards: rank 0's update in front, rank 1's behind
         assert abs(r[4] - (-0.15)) < 1e-6 and abs(r[5] - 0.85) < 1e-6
+
+
+def test_launch_list_summary_splits_at_the_step_boundary(tmp_path):
+    """tools/summarize_profiles.py launches_dram: the last step starts at its patchify launch (the first step carries one-time
+    launches, so halving the list mis-splits); the mean DRAM bytes per ViT GEMM launch go into a JSON keyed by workload,
+    which bench.py reports as roofline.traffic."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("summarize_profiles", os.path.join(root, "tools", "summarize_profiles.py"))
+    sp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sp)
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    rows, i = [hdr], 0
+
+    def launch(name, ns, rd, wr, grid="(148, 1, 1)"):
+        nonlocal i
+        for metric, unit, val in (("dram__bytes_read.sum", "byte", rd), ("dram__bytes_write.sum", "byte", wr),
+                                  ("gpu__time_duration.sum", "ns", ns)):
+            rows.append(f'"{i}","1","python","h","{name}","1","7","(384, 1, 1)","{grid}","0","10.0","s","{metric}","{unit}","{val}"')
+        i += 1
+
+    gemm = "void avt::gemm_bf16_kernel<256, 2, 0, 0, 1>(CUtensorMap_st)"
+    head_wgrad = "void avt::gemm_bf16_kernel<256, 2, 1, 1, 1>(CUtensorMap_st)"
+    for step in range(2):
+        if step == 0:
+            for _ in range(5):
+                launch("avt::cast_f32_bf16_kernel(const float *)", 1000, 10, 10)      # one-time launches of the first step
+        launch("avt::patchify_kernel(const float *)", 17000, 48e6, 24e6)
+        launch(gemm, 60000, 100e6, 20e6)
+        launch(gemm, 40000, 60e6, 20e6)
+        launch(head_wgrad, 15000, 1e6, 30e6)
+        launch("avt::sgd_step_kernel<1>(float *)", 1000000, 3e9, 3e9)
+    src, dst, js = tmp_path / "l.csv", tmp_path / "l.md", tmp_path / "t.json"
+    src.write_text("\n".join(["==PROF== connected"] + rows) + "\n")
+    sp.launches_dram(str(src), str(dst), str(js))
+    text = dst.read_text()
+    assert "5 launches" in text                                   # patchify + 2 GEMMs + head wgrad + ONE sgd launch
+    assert "| `avt::sgd_step_kernel<1>` | 1 |" in text
+    t = json.loads(js.read_text())["vit_base_patch16_224:10:8"]
+    assert t["launches"] == 2 and abs(t["bytes_per_launch"] - 100e6) < 1     # (120 + 80) / 2 MB; the AVT-h weight gradient is left out
